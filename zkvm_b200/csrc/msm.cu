@@ -1,0 +1,814 @@
+// Ristretto255 vartime MSM for sm_100a: kernels, the per-context pipeline and the C ABI (include/zkmsm.h).
+//
+// Pipeline (one MSM = one pass; everything stays in HBM between kernels):
+//   decompress      32 B encodings -> 96 B affine-Niels table entries   (IMAD-bound, ~265 field ops/point)
+//   digits+hist     scalars mod l -> signed radix-2^c digits -> per-(window,bucket) counts (L2 atomics)
+//   scan            exclusive prefix sum over the W*2^(c-1) counts
+//   scatter         point index (+ sign bit) written at its bucket's cursor  = counting sort by bucket
+//   bucket accum    one thread per bucket walks its sorted index run, 7M mixed adds against the Niels table
+//   tree reduce     radix-8 tree per window: (A, Wt) = (plain sum, position-weighted sum) of bucket ranges
+//   window combine  Horner over windows, then RFC 9496 Encode
+//
+// Spec: RFC 9496 for every byte that crosses the ABI; the bucket method itself is the textbook
+// Pippenger/Bernstein algorithm (the result is algorithm-independent: the encoding of a group
+// element is canonical).  No reference source is mounted.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/zkmsm.h"
+#include "ge25519.cuh"
+
+using namespace zk;
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int REDUCE_RADIX_LOG2 = 3;               // tree fan-in 8
+constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
+
+__device__ __forceinline__ void ld_fe(fe& r, const uint4* p) {
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void ld_fe_plain(fe& r, const uint4* p) {   // data written earlier in this stream by another kernel
+    uint4 a = p[0], b = p[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+__device__ __forceinline__ void st_fe(uint4* p, const fe& r) {
+    p[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    p[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void ld_niels(ge_niels& q, const uint4* base, size_t idx) {
+    const uint4* p = base + idx * 6;
+    ld_fe(q.yp, p); ld_fe(q.ym, p + 2); ld_fe(q.t2d, p + 4);
+}
+__device__ __forceinline__ void st_niels(uint4* base, size_t idx, const ge_niels& q) {
+    uint4* p = base + idx * 6;
+    st_fe(p, q.yp); st_fe(p + 2, q.ym); st_fe(p + 4, q.t2d);
+}
+__device__ __forceinline__ void ld_ext(ge_ext& r, const uint4* base, size_t idx) {
+    const uint4* p = base + idx * 8;
+    ld_fe_plain(r.X, p); ld_fe_plain(r.Y, p + 2); ld_fe_plain(r.Z, p + 4); ld_fe_plain(r.T, p + 6);
+}
+__device__ __forceinline__ void st_ext(uint4* base, size_t idx, const ge_ext& r) {
+    uint4* p = base + idx * 8;
+    st_fe(p, r.X); st_fe(p + 2, r.Y); st_fe(p + 4, r.Z); st_fe(p + 6, r.T);
+}
+
+// ---- point-format kernels --------------------------------------------------------------------
+
+// RFC 9496 4.3.1 over a batch; writes affine-Niels entries.  *bad = lowest rejected index.
+__global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
+                                                    unsigned long long* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    fe x, y, t;
+    bool ok = ristretto_decode(x, y, t, w);
+    ge_niels q;
+    if (ok) ge_to_niels_affine(q, x, y, t); else { ge_niels_identity(q); atomicMin(bad, (unsigned long long)i); }
+    st_niels(table, i, q);
+}
+
+// RFC 9496 4.3.4 over a batch of 64-byte strings; normalises to Z = 1 and writes affine-Niels entries.
+__global__ void __launch_bounds__(128) k_from_uniform(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 a = __ldg(in + 4 * i + k);
+        w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
+    }
+    ge_ext p;
+    ristretto_from_uniform(p, w);
+    fe zi, x, y, t;
+    fe_invert(zi, p.Z);
+    fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi); fe_mul(t, x, y);
+    ge_niels q;
+    ge_to_niels_affine(q, x, y, t);
+    st_niels(table, i, q);
+}
+
+__device__ __forceinline__ void niels_to_ext(ge_ext& p, const ge_niels& q) {
+    // (2x : 2y : 2 : 2xy);  T = X*Y/Z = X*Y*2^-1
+    fe inv2 = {{0xfffffff7u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu}};
+    fe_sub(p.X, q.yp, q.ym); fe_add(p.Y, q.yp, q.ym);
+    p.Z = fe_zero(); p.Z.v[0] = 2;
+    fe_mul(p.T, p.X, p.Y); fe_mul(p.T, p.T, inv2);
+}
+
+// RFC 9496 4.3.2 over table entries.
+__global__ void __launch_bounds__(128) k_compress_table(const uint4* __restrict__ table, size_t n, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_niels q; ld_niels(q, table, i);
+    ge_ext p; niels_to_ext(p, q);
+    uint32_t o[8]; ristretto_encode(o, p);
+    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---- scalar recoding ---------------------------------------------------------------------------
+
+// s (any 256-bit value) -> s mod l, l = 2^252 + delta.  q = floor(s / 2^252) over-estimates the quotient by at most 1.
+__device__ __forceinline__ void scalar_reduce(uint32_t s[8]) {
+    const uint32_t DL[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+    uint32_t q = s[7] >> 28;
+    s[7] &= 0x0fffffffu;
+    uint32_t t[5]; uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c += (uint64_t)DL[i] * q; t[i] = (uint32_t)c; c >>= 32; }
+    t[4] = (uint32_t)c;
+    int64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { br += (int64_t)s[i] - (i < 5 ? t[i] : 0u); s[i] = (uint32_t)br; br >>= 32; }
+    uint32_t m = (uint32_t)br;            // 0 or 0xffffffff: went negative -> add l back
+    c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t li = (i < 4 ? DL[i] : (i == 7 ? 0x10000000u : 0u)) & m;
+        c += (uint64_t)s[i] + li; s[i] = (uint32_t)c; c >>= 32;
+    }
+}
+
+// Signed radix-2^c digit w of s (< 2^253), given the carry into this window.  Digits lie in [-2^(c-1), 2^(c-1)].
+__device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c, uint32_t& carry) {
+    int bit = w * c, word = bit >> 5, sh = bit & 31;
+    uint32_t lo = word < 8 ? s[word] : 0u, hi = word + 1 < 8 ? s[word + 1] : 0u;
+    uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & ((1u << c) - 1u);
+    raw += carry;
+    uint32_t half = 1u << (c - 1);
+    carry = raw > half ? 1u : 0u;
+    return (int)raw - (int)(carry << c);
+}
+
+__global__ void __launch_bounds__(256) k_digit_hist(const uint4* __restrict__ scalars, size_t n, int c, int W,
+                                                    uint32_t* __restrict__ counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
+    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    scalar_reduce(s);
+    uint32_t carry = 0; int B = 1 << (c - 1);
+    for (int w = 0; w < W; w++) {
+        int d = next_digit(s, w, c, carry);
+        if (d != 0) atomicAdd(&counts[(size_t)w * B + (abs(d) - 1)], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__ scalars, size_t n, int c, int W,
+                                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
+    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    scalar_reduce(s);
+    uint32_t carry = 0; int B = 1 << (c - 1);
+    for (int w = 0; w < W; w++) {
+        int d = next_digit(s, w, c, carry);
+        if (d != 0) {
+            uint32_t pos = atomicAdd(&cursor[(size_t)w * B + (abs(d) - 1)], 1u);
+            entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ---- exclusive scan over the bucket counts (3 phases, 1024-element tiles) ---------------------
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += t; }
+    return v;
+}
+// exclusive scan of one value per thread across a 256-thread block; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[8];
+    uint32_t inc = warp_incl_scan(v);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { uint32_t x = wsum[k]; if (k < wid) off += x; tot += x; }
+    *total = tot;
+    __syncthreads();
+    return off + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ counts, size_t nb, uint32_t* __restrict__ tile_sums) {
+    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < nb) v += counts[base + k];
+    uint32_t tot; block_excl_scan_256(v, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_scan_tiles(uint32_t* __restrict__ tile_sums, size_t ntiles) {
+    // single block; ntiles <= 256*8
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (size_t base = 0; base < ntiles; base += 256) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0u, tot;
+        uint32_t ex = block_excl_scan_256(v, &tot);
+        uint32_t cb = carry_s;
+        if (i < ntiles) tile_sums[i] = cb + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = cb + tot;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ counts, size_t nb, const uint32_t* __restrict__ tile_offs,
+                                                    uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < nb ? counts[base + k] : 0u; sum += v[k]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_256(sum, &tot) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < nb) { offsets[base + k] = ex; cursor[base + k] = ex; }
+        ex += v[k];
+        if (base + k == nb - 1) offsets[nb] = ex;
+    }
+}
+
+// ---- bucket accumulation ------------------------------------------------------------------------
+
+// One thread per (window, bucket).  entries[offsets[t] .. offsets[t+1]) are the indices (bit 31 = subtract) of
+// the points whose digit in this window has magnitude bucket+1.  Index space: [0, split) -> tab_a, the rest -> tab_b.
+__global__ void __launch_bounds__(128) k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split,
+                                                      const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+                                                      size_t nbuckets, uint4* __restrict__ buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbuckets) return;
+    uint32_t lo = offsets[t], hi = offsets[t + 1];
+    ge_ext acc; ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t k = lo; k < hi; k++) {
+        uint32_t e = entries[k];
+        uint32_t idx = e & 0x7fffffffu;
+        ge_niels q;
+        if (idx < split) ld_niels(q, tab_a, idx); else ld_niels(q, tab_b, idx - split);
+        ge_madd(acc, acc, q, (e >> 31) != 0);
+    }
+    st_ext(buckets, t, acc);
+}
+
+// ---- radix-8 reduction tree ---------------------------------------------------------------------
+// A node covering children i = 0..L-1 (each of width `wc` buckets) combines
+//     A  = sum_i A_i                       (plain sum)
+//     Wt = sum_i Wt_i + wc * sum_i i*A_i   (sum weighted by 1-based position inside the node)
+// At the leaves A_i = Wt_i = bucket i (wc = 1).  The root's Wt is the window sum  sum_b (b+1) * S_b.
+__global__ void __launch_bounds__(128) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in, size_t m_in,
+                                                    size_t m_out, int windows, int log2_wc,
+                                                    uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m_out * (size_t)windows) return;
+    size_t w = t / m_out, k = t % m_out;
+    size_t first = k * REDUCE_RADIX, last = first + REDUCE_RADIX;
+    if (last > m_in) last = m_in;
+    const uint4* ain = a_in + w * m_in * 8;
+    ge_ext run, acc, wsum, tmp;
+    ge_identity(run); ge_identity(acc); ge_identity(wsum);
+    // top-down running sum: after the loop run = sum A_i, acc = sum (i+1) A_i
+#pragma unroll 1
+    for (size_t j = last; j-- > first;) {
+        ld_ext(tmp, ain, j);
+        ge_add(run, run, tmp);
+        ge_add(acc, acc, run);
+    }
+    if (wt_in != nullptr) {
+        // acc - run = sum i*A_i ; scale by wc, add the children's weighted sums
+        ge_neg(tmp, run); ge_add(acc, acc, tmp);
+#pragma unroll 1
+        for (int d = 0; d < log2_wc; d++) ge_dbl(acc, acc);
+        const uint4* win = wt_in + w * m_in * 8;
+#pragma unroll 1
+        for (size_t j = first; j < last; j++) { ld_ext(tmp, win, j); ge_add(wsum, wsum, tmp); }
+        ge_add(acc, acc, wsum);
+    }
+    st_ext(a_out, t, run);
+    st_ext(wt_out, t, acc);
+}
+
+// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  Single thread (253 dependent doublings).
+__global__ void k_window_combine(const uint4* __restrict__ wt, int windows, int c, uint4* __restrict__ out_ext) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ge_ext acc, tmp;
+    ld_ext(acc, wt, windows - 1);
+#pragma unroll 1
+    for (int w = windows - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int d = 0; d < c; d++) ge_dbl(acc, acc);
+        ld_ext(tmp, wt, w);
+        ge_add(acc, acc, tmp);
+    }
+    st_ext(out_ext, 0, acc);
+}
+
+__global__ void k_set_identity(uint4* __restrict__ out_ext) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ge_ext p; ge_identity(p); st_ext(out_ext, 0, p);
+}
+
+// out32 = Encode(sum of g extended points)
+__global__ void k_ext_sum_encode(const uint4* __restrict__ ext, size_t g, uint4* __restrict__ out32) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ge_ext acc, tmp;
+    ge_identity(acc);
+#pragma unroll 1
+    for (size_t i = 0; i < g; i++) { ld_ext(tmp, ext, i); ge_add(acc, acc, tmp); }
+    uint32_t o[8]; ristretto_encode(o, acc);
+    out32[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    out32[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---- integer-pipe microbenchmarks ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bench_imad_wide(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+        // two independent 4-slot carry chains per statement, the shape fe_mul issues
+        asm volatile(
+            "mad.lo.cc.u32 %0, %16, %17, %0; madc.hi.cc.u32 %1, %16, %17, %1; madc.lo.cc.u32 %2, %16, %17, %2; madc.hi.cc.u32 %3, %16, %17, %3;"
+            "madc.lo.cc.u32 %4, %16, %17, %4; madc.hi.cc.u32 %5, %16, %17, %5; madc.lo.cc.u32 %6, %16, %17, %6; madc.hi.u32 %7, %16, %17, %7;"
+            "mad.lo.cc.u32 %8, %17, %16, %8; madc.hi.cc.u32 %9, %17, %16, %9; madc.lo.cc.u32 %10, %17, %16, %10; madc.hi.cc.u32 %11, %17, %16, %11;"
+            "madc.lo.cc.u32 %12, %17, %16, %12; madc.hi.cc.u32 %13, %17, %16, %13; madc.lo.cc.u32 %14, %17, %16, %14; madc.hi.u32 %15, %17, %16, %15;"
+            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+              "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+            : "r"(a), "r"(b));
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x ^= r[i];
+    if (x == 0x12345678u) out[0] = x;   // keep the chain live
+}
+__global__ void __launch_bounds__(256) k_bench_imad32(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= r[i];
+    if (x == 0x12345678u) out[0] = x;
+}
+__global__ void __launch_bounds__(256) k_bench_fe(uint32_t* out, int iters, uint32_t seed, int square) {
+    fe x, y;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x.v[i] = seed * (i + 1) + threadIdx.x; y.v[i] = seed * (i + 7) + blockIdx.x; }
+    if (square) {
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) { fe_sqr(x, x); fe_sqr(y, y); }
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) { fe_mul(x, x, y); fe_mul(y, y, x); }
+    }
+    uint32_t z = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) z ^= x.v[i] ^ y.v[i];
+    if (z == 0x12345678u) out[0] = z;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side: context, workspace, pipeline
+// ------------------------------------------------------------------------------------------------
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+};
+
+struct zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[256] = {0};
+    int forced_window = 0;
+    int profiling = 0;
+    float phase_ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t launches = 0;
+    // workspace
+    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, buckets, tree_a, tree_w, out_ext, out32, bad;
+    uint8_t* h_out = nullptr;               // pinned 64 B: [0,32) encoding, [32,40) bad index
+};
+
+struct zk_table {
+    int device = 0;
+    uint4* d = nullptr;
+    size_t len = 0, cap = 0;
+};
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return e_ == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA;                    \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)            \
+    do {                             \
+        (ctx)->launches++;           \
+        CK(ctx, cudaGetLastError()); \
+    } while (0)
+
+static int ensure(zk_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return ZK_OK;
+    if (b.p) { CK(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;
+    CK(ctx, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return ZK_OK;
+}
+#define TRY(x) do { int rc_ = (x); if (rc_ != ZK_OK) return rc_; } while (0)
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" int zk_abi_version(void) { return ZK_ABI_VERSION; }
+
+extern "C" const char* zk_status_str(int s) {
+    switch (s) {
+        case ZK_OK: return "ok";
+        case ZK_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
+        case ZK_ERR_INVALID_POINT: return "invalid ristretto255 encoding";
+        case ZK_ERR_ARG: return "bad argument";
+        case ZK_ERR_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+extern "C" const char* zk_last_error(const zk_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+extern "C" int zk_ctx_create(int device, zk_ctx** out) {
+    if (!out) return ZK_ERR_ARG;
+    *out = nullptr;
+    zk_ctx* ctx = new (std::nothrow) zk_ctx();
+    if (!ctx) return ZK_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_out, 64);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "zkmsm: cannot create context on CUDA device %d: %s (there is no CPU fallback)\n", device,
+                cudaGetErrorString(e));
+        delete ctx;
+        return ZK_ERR_CUDA;
+    }
+    *out = ctx;
+    return ZK_OK;
+}
+
+extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->scalars, &ctx->comp, &ctx->dyn_table, &ctx->counts, &ctx->cursor, &ctx->offsets, &ctx->tiles,
+                      &ctx->entries, &ctx->buckets, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int zk_ctx_sync(zk_ctx* ctx) {
+    if (!ctx) return ZK_ERR_ARG;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+extern "C" void* zk_ctx_stream(zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int zk_ctx_set_window(zk_ctx* ctx, int c) {
+    if (!ctx || (c != 0 && (c < 4 || c > 16))) return ZK_ERR_ARG;
+    ctx->forced_window = c;
+    return ZK_OK;
+}
+extern "C" int zk_ctx_set_profiling(zk_ctx* ctx, int on) { if (!ctx) return ZK_ERR_ARG; ctx->profiling = on; return ZK_OK; }
+extern "C" int zk_ctx_last_phase_ms(zk_ctx* ctx, float out_ms[4]) {
+    if (!ctx || !out_ms) return ZK_ERR_ARG;
+    for (int i = 0; i < 4; i++) out_ms[i] = ctx->phase_ms[i];
+    return ZK_OK;
+}
+extern "C" uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Window width by size: minimise W*(7n + 18*2^(c-1)) field multiplies subject to enough buckets to fill the chip.
+extern "C" int zk_pick_window(size_t n) {
+    int best = 4; double best_cost = 1e300;
+    for (int c = 4; c <= 16; c++) {
+        double W = 253 / c + 1, B = (double)(1u << (c - 1));
+        double cost = W * (7.0 * (double)n + 18.0 * B);
+        // a bucket thread is a serial chain of n/B adds: charge the chain when the grid cannot fill 148 SMs x 512 threads
+        double threads = W * B;
+        if (threads < 148.0 * 512.0) cost *= (148.0 * 512.0) / threads > 8.0 ? 8.0 : (148.0 * 512.0) / threads;
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+// ---- tables ----
+extern "C" int zk_table_create(zk_ctx* ctx, size_t capacity, zk_table** out) {
+    if (!ctx || !out) return ZK_ERR_ARG;
+    *out = nullptr;
+    zk_table* t = new (std::nothrow) zk_table();
+    if (!t) return ZK_ERR_NOMEM;
+    t->device = ctx->device;
+    t->cap = capacity ? capacity : 1;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&t->d, t->cap * 96);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "zk_table_create: %s", cudaGetErrorString(e));
+        delete t;
+        return e == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA;
+    }
+    *out = t;
+    return ZK_OK;
+}
+extern "C" void zk_table_destroy(zk_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->d) cudaFree(t->d);
+    delete t;
+}
+extern "C" size_t zk_table_len(const zk_table* t) { return t ? t->len : 0; }
+extern "C" size_t zk_table_capacity(const zk_table* t) { return t ? t->cap : 0; }
+extern "C" void zk_table_clear(zk_table* t) { if (t) t->len = 0; }
+
+static int table_reserve(zk_ctx* ctx, zk_table* t, size_t need) {
+    if (need <= t->cap) return ZK_OK;
+    size_t cap = t->cap * 2 > need ? t->cap * 2 : need;
+    uint4* nd = nullptr;
+    CK(ctx, cudaMalloc((void**)&nd, cap * 96));
+    if (t->len) CK(ctx, cudaMemcpyAsync(nd, t->d, t->len * 96, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaFree(t->d));
+    t->d = nd; t->cap = cap;
+    return ZK_OK;
+}
+
+// decompress n encodings at `src_dev` into table rows [dst_row, dst_row+n); returns INVALID_POINT + index on reject.
+static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* table, size_t dst_row, size_t* bad_index, bool sync) {
+    if (n == 0) return ZK_OK;
+    TRY(ensure(ctx, ctx->bad, 8));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
+    k_decompress<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
+                                                             (unsigned long long*)ctx->bad.p);
+    LAUNCH_CHECK(ctx);
+    if (!sync) return ZK_OK;
+    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
+    if (b != ~0ull) { if (bad_index) *bad_index = (size_t)b; return ZK_ERR_INVALID_POINT; }
+    return ZK_OK;
+}
+
+extern "C" int zk_table_append_compressed_dev(zk_ctx* ctx, zk_table* t, const void* points32_dev, size_t n, size_t* bad_index) {
+    if (!ctx || !t || (!points32_dev && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(table_reserve(ctx, t, t->len + n));
+    TRY(decompress_into(ctx, points32_dev, n, t->d, t->len, bad_index, true));
+    t->len += n;
+    return ZK_OK;
+}
+extern "C" int zk_table_append_compressed(zk_ctx* ctx, zk_table* t, const uint8_t* points32_host, size_t n, size_t* bad_index) {
+    if (!ctx || !t || (!points32_host && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->comp, n * 32));
+    CK(ctx, cudaMemcpyAsync(ctx->comp.p, points32_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return zk_table_append_compressed_dev(ctx, t, ctx->comp.p, n, bad_index);
+}
+extern "C" int zk_table_append_uniform_dev(zk_ctx* ctx, zk_table* t, const void* bytes64_dev, size_t n) {
+    if (!ctx || !t || (!bytes64_dev && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(table_reserve(ctx, t, t->len + n));
+    if (n) {
+        k_from_uniform<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)bytes64_dev, n, t->d + t->len * 6);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    t->len += n;
+    return ZK_OK;
+}
+extern "C" int zk_table_append_uniform(zk_ctx* ctx, zk_table* t, const uint8_t* bytes64_host, size_t n) {
+    if (!ctx || !t || (!bytes64_host && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->comp, n * 64));
+    CK(ctx, cudaMemcpyAsync(ctx->comp.p, bytes64_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    return zk_table_append_uniform_dev(ctx, t, ctx->comp.p, n);
+}
+extern "C" int zk_table_compress_dev(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, void* out32_dev) {
+    if (!ctx || !t || (!out32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n) {
+        k_compress_table<<<grid_for(n, 128), 128, 0, ctx->stream>>>(t->d + offset * 6, n, (uint4*)out32_dev);
+        LAUNCH_CHECK(ctx);
+    }
+    return ZK_OK;
+}
+extern "C" int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, uint8_t* out32_host) {
+    if (!ctx || !t || (!out32_host && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->comp, n * 32 + 32));
+    TRY(zk_table_compress_dev(ctx, t, offset, n, ctx->comp.p));
+    CK(ctx, cudaMemcpyAsync(out32_host, ctx->comp.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+// ---- the MSM pipeline (asynchronous on ctx->stream) ----
+// scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
+static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split, size_t n,
+                        void* out_ext_dev) {
+    cudaStream_t st = ctx->stream;
+    if (n == 0) {
+        k_set_identity<<<1, 32, 0, st>>>((uint4*)out_ext_dev);
+        LAUNCH_CHECK(ctx);
+        return ZK_OK;
+    }
+    if (n >= (1ull << 31)) return ZK_ERR_ARG;
+    const int c = ctx->forced_window ? ctx->forced_window : zk_pick_window(n);
+    const int W = 253 / c + 1;
+    const size_t B = (size_t)1 << (c - 1);
+    const size_t NB = B * W;
+    const size_t ntiles = (NB + 1023) / 1024;
+
+    TRY(ensure(ctx, ctx->counts, NB * 4));
+    TRY(ensure(ctx, ctx->cursor, NB * 4));
+    TRY(ensure(ctx, ctx->offsets, (NB + 1) * 4));
+    TRY(ensure(ctx, ctx->tiles, ntiles * 4));
+    TRY(ensure(ctx, ctx->entries, n * W * 4));
+    TRY(ensure(ctx, ctx->buckets, NB * 128));
+    size_t m1 = (B + REDUCE_RADIX - 1) / REDUCE_RADIX;
+    TRY(ensure(ctx, ctx->tree_a, 2 * m1 * W * 128));     // ping-pong halves
+    TRY(ensure(ctx, ctx->tree_w, 2 * m1 * W * 128));
+
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
+    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
+    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->counts.p);
+    LAUNCH_CHECK(ctx);
+    k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (uint32_t*)ctx->tiles.p);
+    LAUNCH_CHECK(ctx);
+    k_scan_tiles<<<1, 256, 0, st>>>((uint32_t*)ctx->tiles.p, ntiles);
+    LAUNCH_CHECK(ctx);
+    k_scan_apply<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (const uint32_t*)ctx->tiles.p,
+                                                    (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p);
+    LAUNCH_CHECK(ctx);
+    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->cursor.p,
+                                                       (uint32_t*)ctx->entries.p);
+    LAUNCH_CHECK(ctx);
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
+
+    k_bucket_accum<<<grid_for(NB, 128), 128, 0, st>>>(tab_a, tab_b, (uint32_t)split, (const uint32_t*)ctx->entries.p,
+                                                       (const uint32_t*)ctx->offsets.p, NB, (uint4*)ctx->buckets.p);
+    LAUNCH_CHECK(ctx);
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[3], st));
+
+    // radix-8 tree, per window, until one node is left
+    const uint4* a_in = (const uint4*)ctx->buckets.p;
+    const uint4* w_in = nullptr;
+    size_t m_in = B; int log2_wc = 0; int half = 0;
+    while (true) {
+        size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
+        uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
+        uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
+        k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, W, log2_wc, a_out, w_out);
+        LAUNCH_CHECK(ctx);
+        a_in = a_out; w_in = w_out; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
+        if (m_out == 1) break;
+    }
+    k_window_combine<<<1, 32, 0, st>>>(w_in, W, c, (uint4*)out_ext_dev);
+    LAUNCH_CHECK(ctx);
+    return ZK_OK;
+}
+
+static int finish_encode(zk_ctx* ctx, const void* ext_dev, size_t g, uint8_t out32[32]) {
+    TRY(ensure(ctx, ctx->out32, 32));
+    k_ext_sum_encode<<<1, 32, 0, ctx->stream>>>((const uint4*)ext_dev, g, (uint4*)ctx->out32.p);
+    LAUNCH_CHECK(ctx);
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out32, ctx->h_out, 32);
+    if (ctx->profiling) {
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
+        }
+    }
+    return ZK_OK;
+}
+
+extern "C" int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk_table* t, size_t offset, size_t n, void* out_ext128_dev) {
+    if (!ctx || !t || !out_ext128_dev || (!scalars32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->profiling) { CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream)); }
+    return msm_pipeline(ctx, scalars32_dev, t->d + offset * 6, nullptr, n, n, out_ext128_dev);
+}
+
+extern "C" int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]) {
+    if (!ctx || (!ext128_dev && g) || !out32) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int prof = ctx->profiling; ctx->profiling = 0;
+    int rc = finish_encode(ctx, ext128_dev, g, out32);
+    ctx->profiling = prof;
+    return rc;
+}
+
+extern "C" int zk_msm_vartime_table(zk_ctx* ctx, const uint8_t* scalars32_host, const zk_table* t, size_t offset, size_t n, uint8_t out32[32]) {
+    if (!ctx || !t || !out32 || (!scalars32_host && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->scalars, n * 32));
+    TRY(ensure(ctx, ctx->out_ext, 128));
+    if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    TRY(msm_pipeline(ctx, ctx->scalars.p, t->d + offset * 6, nullptr, n, n, ctx->out_ext.p));
+    if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], ctx->stream));
+    return finish_encode(ctx, ctx->out_ext.p, 1, out32);
+}
+
+extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32_host, const zk_table* t, size_t offset, size_t n_static,
+                                    const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, uint8_t out32[32]) {
+    if (!ctx || !out32) return ZK_ERR_ARG;
+    if (n_static && (!t || !scalars_static32_host || offset > t->len || n_static > t->len - offset)) return ZK_ERR_ARG;
+    if (n_dyn && (!scalars_dyn32_host || !points_dyn32_host)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    size_t n = n_static + n_dyn;
+    TRY(ensure(ctx, ctx->scalars, n * 32));
+    TRY(ensure(ctx, ctx->out_ext, 128));
+    TRY(ensure(ctx, ctx->comp, n_dyn * 32));
+    TRY(ensure(ctx, ctx->dyn_table, n_dyn * 96));
+    TRY(ensure(ctx, ctx->bad, 8));
+    cudaStream_t st = ctx->stream;
+    if (n_static) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_static32_host, n_static * 32, cudaMemcpyHostToDevice, st));
+    if (n_dyn) {
+        CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->comp.p, points_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
+    }
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], st));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
+    TRY(decompress_into(ctx, ctx->comp.p, n_dyn, (uint4*)ctx->dyn_table.p, 0, nullptr, false));
+    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));
+    const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
+    TRY(msm_pipeline(ctx, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, n, ctx->out_ext.p));
+    if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], st));
+    TRY(finish_encode(ctx, ctx->out_ext.p, 1, out32));
+    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
+    if (n_dyn && b != ~0ull) { memset(out32, 0, 32); return ZK_ERR_INVALID_POINT; }
+    return ZK_OK;
+}
+
+extern "C" int zk_msm_vartime(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, size_t n, uint8_t out32[32]) {
+    return zk_msm_vartime_mixed(ctx, nullptr, nullptr, 0, 0, scalars32_host, points32_host, n, out32);
+}
+
+extern "C" int zk_encoding_is_identity(const uint8_t enc32[32]) {
+    if (!enc32) return 0;
+    uint8_t o = 0;
+    for (int i = 0; i < 32; i++) o |= enc32[i];
+    return o == 0;
+}
+
+extern "C" int zk_bench_int_pipe(zk_ctx* ctx, int kind, double* ops_per_sec) {
+    if (!ctx || !ops_per_sec || kind < 0 || kind > 3) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->out32, 32));
+    int dev_sms = 0;
+    CK(ctx, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int blocks = dev_sms * 8, threads = 256;
+    const int iters = kind <= 1 ? 4096 : 512;
+    double per_thread = kind == 0 ? 8.0 * iters : kind == 1 ? 8.0 * iters : 2.0 * iters;
+    cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(ctx, cudaEventRecord(a, ctx->stream));
+        if (kind == 0) k_bench_imad_wide<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->out32.p, iters, 12345u + rep);
+        else if (kind == 1) k_bench_imad32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->out32.p, iters, 12345u + rep);
+        else k_bench_fe<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->out32.p, iters, 12345u + rep, kind == 3);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaEventRecord(b, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0; CK(ctx, cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *ops_per_sec = per_thread * blocks * threads / (best * 1e-3);
+    return ZK_OK;
+}
