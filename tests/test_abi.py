@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/zkmsm.h declares; without a GPU every entry
+point that needs one fails loudly (no CPU fallback).  CPU only -- no compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "zkmsm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from zkvm_b200 import _lib
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/zkmsm.h but not exported by libzkmsm.so"
+    assert sorted(s[0] for s in _lib.SYMBOLS) == names, "ctypes table and header disagree"
+
+
+def test_no_torch_types_in_abi():
+    src = open(os.path.join(ROOT, "include", "zkmsm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)      # signatures only, not the prose
+    assert "torch" not in src.lower() and "at::" not in src and "#include <cuda" not in src
+
+
+def test_host_only_entry_points():
+    from zkvm_b200 import _lib
+    lib = _lib.load()
+    assert lib.zk_abi_version() == 1
+    assert lib.zk_encoding_is_identity(bytes(32)) == 1
+    assert lib.zk_encoding_is_identity(bytes([1]) + bytes(31)) == 0
+    assert b"invalid" in lib.zk_status_str(_lib.ZK_ERR_INVALID_POINT)
+    for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24):
+        assert 4 <= lib.zk_pick_window(n) <= 16
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reach into oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "zkvm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "msm_oracle" not in txt and "libsodium" not in txt.lower(), f
+
+
+def test_context_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure path is for GPU-less hosts")
+    import zkvm_b200 as zk
+    with pytest.raises(zk.ZkError) as e:
+        zk.Context(0)
+    assert "no CPU fallback" in str(e.value)

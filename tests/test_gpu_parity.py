@@ -1,0 +1,217 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the golden vectors, and -- at the full
+BASELINE.json sizes -- size-independent properties.  Bit-exact: every comparison is on bytes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+def le32(v):
+    return (v % 2**256).to_bytes(32, "little")
+
+
+def make_points(c_oracle, n, seed):
+    rng = np.random.default_rng(seed)
+    return c_oracle.from_uniform(rng.integers(0, 256, size=(n, 64), dtype=np.uint8), n)
+
+
+def rand_scalars(n, seed):
+    return np.random.default_rng(seed ^ 0xabc).integers(0, 256, size=(n, 32), dtype=np.uint8)
+
+
+# ---------------- codec ----------------
+def test_decode_encode_golden(ctx, rfc_vectors):
+    import zkvm_b200 as zk
+    enc = b"".join(H(h) for h in rfc_vectors["generator_multiples"])
+    t = zk.PointTable(ctx).append_compressed(enc)
+    assert len(t) == 16
+    assert t.compress() == enc
+    assert t.compress(offset=3, n=2) == enc[96:160]
+
+
+def test_bad_encodings_rejected_with_index(ctx, rfc_vectors):
+    import zkvm_b200 as zk
+    good = H(rfc_vectors["generator_multiples"][5])
+    for cat, lst in rfc_vectors["bad_encodings"].items():
+        for k, h in enumerate(lst):
+            t = zk.PointTable(ctx)
+            blob = good * (k + 2) + H(h) + good * 3 + H(h)
+            with pytest.raises(zk.InvalidPoint) as e:
+                t.append_compressed(blob)
+            assert e.value.index == k + 2, (cat, h)
+            assert len(t) == 0
+            assert zk.CompressedRistretto(H(h)).decompress(ctx) is None
+            assert zk.RistrettoPoint.optional_multiscalar_mul(ctx, le32(1) * 2, good + H(h)) is None
+
+
+def test_validity_matches_sodium(ctx, sodium_vectors):
+    import zkvm_b200 as zk
+    for b, ok in sodium_vectors["validity"]:
+        assert (zk.CompressedRistretto(H(b)).decompress(ctx) is not None) == ok
+
+
+def test_from_uniform_golden_and_oracle(ctx, rfc_vectors, sodium_vectors, c_oracle):
+    import zkvm_b200 as zk
+    t = zk.PointTable(ctx).append_uniform(b"".join(H(h) for h, _ in sodium_vectors["from_hash"]))
+    assert t.compress() == b"".join(H(e) for _, e in sodium_vectors["from_hash"])
+    for v in rfc_vectors["derivation"]:
+        assert zk.PointTable(ctx).append_uniform(H(v["sha512"])).compress().hex() == v["element"]
+    u = np.random.default_rng(11).integers(0, 256, size=(5000, 64), dtype=np.uint8)
+    t = zk.PointTable(ctx, 5000).append_uniform(u)
+    enc = t.compress()
+    assert enc == c_oracle.from_uniform(u, 5000)
+    assert zk.PointTable(ctx).append_compressed(enc).compress() == enc      # decode(encode(P)) == P
+
+
+# ---------------- MSM vs golden / oracle ----------------
+def test_msm_sodium_golden(ctx, sodium_vectors):
+    import zkvm_b200 as zk
+    for case in sodium_vectors["msm"]:
+        s = b"".join(H(x) for x in case["scalars"]); p = b"".join(H(x) for x in case["points"])
+        for c in (0, 4, 9, 16):
+            ctx.set_window(c)
+            got = zk.RistrettoPoint.optional_multiscalar_mul(ctx, s, p)
+            assert bytes(got).hex() == case["result"], (len(case["scalars"]), c)
+    ctx.set_window(0)
+
+
+def test_scalarmult_golden_edge_scalars(ctx, sodium_vectors):
+    """n = 1 MSMs with scalars 0, 1, l-1, l, l+1, 2^255, 2^256-1, ... (unreduced scalars are taken mod l)."""
+    import zkvm_b200 as zk
+    for k, p, r in sodium_vectors["scalarmult"]:
+        assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, H(k), H(p))).hex() == r
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 189, 190, 1000, 4097, 1 << 14])
+def test_msm_vs_oracle_all_windows(ctx, c_oracle, n):
+    import zkvm_b200 as zk
+    pts = make_points(c_oracle, n, n); sc = rand_scalars(n, n)
+    want = c_oracle.msm(sc, pts, n, threads=4)
+    tab = zk.PointTable(ctx, n).append_compressed(pts)
+    for c in (0, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16):
+        ctx.set_window(c)
+        assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want, c
+        assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want, c
+    ctx.set_window(0)
+
+
+def test_msm_adversarial_inputs(ctx, c_oracle):
+    """All-identity points, one repeated point, scalars 0 / 1 / l-1, everything in one bucket."""
+    import zkvm_b200 as zk
+    n = 3000
+    pts = make_points(c_oracle, n, 99)
+    cases = {
+        "all identity points": (rand_scalars(n, 1).tobytes(), bytes(32) * n),
+        "repeated point": (rand_scalars(n, 2).tobytes(), pts[:32] * n),
+        "scalars all zero": (bytes(32 * n), pts),
+        "scalars all one": (le32(1) * n, pts),
+        "scalars all l-1": (le32(L - 1) * n, pts),
+        "scalars all equal random": (le32(0x1234567890abcdef << 100 | 77) * n, pts),
+        "scalars 0,1,l-1 cycling": (b"".join(le32(v) for v in (0, 1, L - 1)) * (n // 3), pts),
+        "single high window": (le32(1 << 251) * n, pts),
+    }
+    for name, (s, p) in cases.items():
+        want = c_oracle.msm(s, p, n, threads=4)
+        for c in (0, 8, 16):
+            ctx.set_window(c)
+            assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, s, p)) == want, (name, c)
+    ctx.set_window(0)
+    assert want is not None
+    assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, b"", b"")) == bytes(32)     # empty MSM = identity
+
+
+def test_invalid_point_anywhere_rejects(ctx, c_oracle, rfc_vectors):
+    import zkvm_b200 as zk
+    n = 2048
+    pts = bytearray(make_points(c_oracle, n, 5)); sc = rand_scalars(n, 5)
+    bad = H(rfc_vectors["bad_encodings"]["negative_xy"][2])
+    for idx in (0, 777, n - 1):
+        q = bytearray(pts); q[32 * idx:32 * idx + 32] = bad
+        assert zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, bytes(q)) is None
+        assert c_oracle.msm(sc, bytes(q), n) is None
+    assert zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, bytes(pts)) is not None
+
+
+def test_table_slices_and_mixed(ctx, c_oracle):
+    """Cached static prefix + dynamic compressed suffix (the bulletproofs verification shape)."""
+    import zkvm_b200 as zk
+    n_s, n_d = 1500, 300
+    gens = make_points(c_oracle, 4000, 21); dyn = make_points(c_oracle, n_d, 22)
+    s_s = rand_scalars(n_s, 23); s_d = rand_scalars(n_d, 24)
+    tab = zk.PointTable(ctx).append_compressed(gens[:32 * 1000]).append_compressed(gens[32 * 1000:])   # growth path
+    assert len(tab) == 4000
+    off = 700
+    want = c_oracle.msm(s_s.tobytes() + s_d.tobytes(), gens[32 * off:32 * (off + n_s)] + dyn, n_s + n_d, threads=4)
+    got = zk.RistrettoPoint.mixed_multiscalar_mul(ctx, s_s, tab, s_d, dyn, offset=off)
+    assert bytes(got) == want
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, s_s, tab, offset=off)) == \
+        c_oracle.msm(s_s, gens[32 * off:32 * (off + n_s)], n_s, threads=4)
+    # only static / only dynamic
+    assert bytes(zk.RistrettoPoint.mixed_multiscalar_mul(ctx, s_s, tab, b"", b"", offset=off)) == \
+        c_oracle.msm(s_s, gens[32 * off:32 * (off + n_s)], n_s, threads=4)
+    assert bytes(zk.RistrettoPoint.mixed_multiscalar_mul(ctx, b"", None, s_d, dyn)) == c_oracle.msm(s_d, dyn, n_d)
+    with pytest.raises(zk.ZkError):
+        zk.RistrettoPoint.vartime_multiscalar_mul(ctx, s_s, tab, offset=3000)       # slice out of range
+
+
+# ---------------- full-size properties (n = 2^20, the headline config) ----------------
+@pytest.fixture(scope="module")
+def big(ctx):
+    import zkvm_b200 as zk
+    n = 1 << 20
+    u = np.random.default_rng(2020).integers(0, 256, size=(n, 64), dtype=np.uint8)
+    tab = zk.PointTable(ctx, n).append_uniform(u)
+    return n, tab, tab.compress(), rand_scalars(n, 2020)
+
+
+def test_big_window_independence_and_compressed_path(ctx, big):
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    res = set()
+    for c in (13, 15, 16, 0):
+        ctx.set_window(c)
+        res.add(bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)))
+    ctx.set_window(0)
+    res.add(bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, comp)))     # decompress-on-device path
+    assert len(res) == 1
+
+
+def test_big_negation_cancels(ctx, big):
+    """sum s_i P_i + sum (l - s_i) P_i = identity: one 2^21-point MSM that must encode to 32 zero bytes."""
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    half = 1 << 19
+    s_int = [int.from_bytes(bytes(r), "little") % L for r in sc[:half]]
+    neg = b"".join(le32(L - v) for v in s_int)
+    out = zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc[:half].tobytes() + neg, comp[:32 * half] * 2)
+    assert out.is_identity()
+
+
+def test_big_linearity_against_oracle_scalarmult(ctx, big, c_oracle):
+    """MSM(k * 1, P) == k * MSM(1, P): the right side is one oracle scalar multiplication of the GPU's point sum."""
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    total = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, le32(1) * n, tab)
+    k = 0x0123456789abcdef0123456789abcdef0123456789abcdef0123456789abcdef % L
+    got = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, le32(k) * n, tab)
+    assert bytes(got) == c_oracle.scalarmult(le32(k), bytes(total))
+
+
+def test_big_split_sums_to_whole(ctx, big, c_oracle):
+    """Index-range partial MSMs add up to the whole (the multi-GPU sharding identity), checked by the oracle."""
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    whole = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)
+    cuts = [0, 100000, 1 << 19, n - 3, n]
+    parts = b"".join(bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[a:b], tab, offset=a)) for a, b in zip(cuts, cuts[1:]))
+    assert c_oracle.point_sum(parts, len(cuts) - 1) == bytes(whole)
+
+
+def test_sample_of_big_against_oracle(ctx, big, c_oracle):
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    m = 1 << 15
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[5000:5000 + m], tab, offset=5000)) == \
+        c_oracle.msm(sc[5000:5000 + m], comp[32 * 5000:32 * (5000 + m)], m, threads=8)

@@ -1,0 +1,91 @@
+"""The oracles (big-integer Python + C restatement) against the golden vectors.  CPU only.
+
+This is what pins the oracle: RFC 9496 Appendix A (re-verified transcription) and libsodium 1.0.20
+known answers -- the reference itself has no fixtures."""
+import numpy as np
+import pytest
+
+from oracle import ristretto255_ref as ref
+
+H = bytes.fromhex
+
+
+def test_py_generator_multiples(rfc_vectors):
+    acc = ref.Point.identity()
+    for h in rfc_vectors["generator_multiples"]:
+        assert acc.encode().hex() == h
+        assert ref.decode(H(h)).encode().hex() == h
+        acc = acc + ref.BASEPOINT
+    assert len(rfc_vectors["generator_multiples"]) == 16
+
+
+def test_py_bad_encodings(rfc_vectors):
+    n = 0
+    for cat, lst in rfc_vectors["bad_encodings"].items():
+        for h in lst:
+            assert ref.decode(H(h)) is None, (cat, h)
+            n += 1
+    assert n == 29
+
+
+def test_py_derivation(rfc_vectors):
+    for v in rfc_vectors["derivation"]:
+        assert ref.from_uniform_bytes(H(v["sha512"])).encode().hex() == v["element"]
+
+
+def test_py_vs_sodium(sodium_vectors):
+    for h, e in sodium_vectors["from_hash"]:
+        assert ref.from_uniform_bytes(H(h)).encode().hex() == e
+    for k, p, r in sodium_vectors["scalarmult"][:20]:
+        assert (ref.decode(H(p)) * int.from_bytes(H(k), "little")).encode().hex() == r
+    for b, ok in sodium_vectors["validity"]:
+        assert (ref.decode(H(b)) is not None) == ok
+    for case in sodium_vectors["msm"][:6]:
+        got = ref.msm_naive([H(s) for s in case["scalars"]], [H(p) for p in case["points"]])
+        assert got.hex() == case["result"]
+
+
+def test_c_generator_multiples_and_bad(rfc_vectors, c_oracle):
+    B = H(rfc_vectors["generator_multiples"][1])
+    for i, h in enumerate(rfc_vectors["generator_multiples"]):
+        assert c_oracle.scalarmult(i.to_bytes(32, "little"), B).hex() == h
+        assert c_oracle.is_valid(H(h))
+    for cat, lst in rfc_vectors["bad_encodings"].items():
+        for h in lst:
+            assert not c_oracle.is_valid(H(h)), (cat, h)
+            assert c_oracle.msm(bytes(32), H(h), 1) is None
+
+
+def test_c_vs_sodium(sodium_vectors, c_oracle):
+    blob = b"".join(H(h) for h, _ in sodium_vectors["from_hash"])
+    got = c_oracle.from_uniform(blob, len(sodium_vectors["from_hash"]))
+    assert got == b"".join(H(e) for _, e in sodium_vectors["from_hash"])
+    for k, p, r in sodium_vectors["scalarmult"]:
+        assert c_oracle.scalarmult(H(k), H(p)).hex() == r
+    for b, ok in sodium_vectors["validity"]:
+        assert c_oracle.is_valid(H(b)) == ok
+    for case in sodium_vectors["msm"]:
+        n = len(case["scalars"])
+        s = b"".join(H(x) for x in case["scalars"]); p = b"".join(H(x) for x in case["points"])
+        for threads in (1, 3):
+            assert c_oracle.msm(s, p, n, threads).hex() == case["result"], n
+
+
+@pytest.mark.parametrize("n,threads", [(150, 1), (190, 1), (700, 2), (1500, 1), (3000, 4)])
+def test_c_msm_algorithms_agree_with_scalarmult_sum(c_oracle, n, threads):
+    """Straus (n<190) and Pippenger (each digit width) against sum of independent double-and-add products."""
+    rng = np.random.default_rng(n)
+    pts = c_oracle.from_uniform(rng.integers(0, 256, size=(n, 64), dtype=np.uint8), n)
+    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    prods = b"".join(c_oracle.scalarmult(bytes(sc[i]), pts[32 * i:32 * i + 32]) for i in range(n))
+    assert c_oracle.msm(sc, pts, n, threads) == c_oracle.point_sum(prods, n)
+
+
+def test_c_decompress_reports_first_bad_index(c_oracle, rfc_vectors):
+    good = H(rfc_vectors["generator_multiples"][3])
+    bad = H(rfc_vectors["bad_encodings"]["non_square"][0])
+    blob = good * 10 + bad + good * 5 + bad
+    _, idx = c_oracle.decompress(blob, 17, threads=1)
+    assert idx == 10
+    _, idx = c_oracle.decompress(good * 17, 17, threads=2)
+    assert idx is None

@@ -1,0 +1,94 @@
+// Header-only C++ host mirror of the reference-facing API for the MSM hot path, over the C ABI in
+// include/zkmsm.h.  Names follow curve25519-dalek's public items for this path (CompressedRistretto,
+// Scalar, VartimeMultiscalarMul::{vartime_multiscalar_mul, optional_multiscalar_mul}) as recalled from
+// public knowledge -- the upstream source is not mounted, so there is no file:line
+// to cite.  Nothing is computed on the CPU here; every call forwards to libzkmsm.so.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/zkmsm.h"
+
+namespace zkvm_b200 {
+
+using Scalar = std::array<uint8_t, 32>;               // little-endian, taken modulo the group order
+using CompressedRistretto = std::array<uint8_t, 32>;  // RFC 9496 encoding
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        int rc = zk_ctx_create(device, &h_);
+        if (rc != ZK_OK) throw Error(rc, std::string("zk_ctx_create: ") + zk_status_str(rc) + " (no CPU fallback)");
+    }
+    ~Context() { zk_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    zk_ctx* raw() const { return h_; }
+    void check(int rc) const {
+        if (rc != ZK_OK) throw Error(rc, std::string(zk_status_str(rc)) + ": " + zk_last_error(h_));
+    }
+  private:
+    zk_ctx* h_ = nullptr;
+};
+
+// Device-resident Vec<RistrettoPoint>.
+class PointTable {
+  public:
+    PointTable(Context& ctx, size_t capacity = 0) : ctx_(ctx) { ctx_.check(zk_table_create(ctx.raw(), capacity, &h_)); }
+    ~PointTable() { zk_table_destroy(h_); }
+    PointTable(const PointTable&) = delete;
+    PointTable& operator=(const PointTable&) = delete;
+    size_t size() const { return zk_table_len(h_); }
+    // Returns the index of the first invalid encoding, or nullopt when all n were appended.
+    std::optional<size_t> append_compressed(const CompressedRistretto* pts, size_t n) {
+        size_t bad = 0;
+        int rc = zk_table_append_compressed(ctx_.raw(), h_, reinterpret_cast<const uint8_t*>(pts), n, &bad);
+        if (rc == ZK_ERR_INVALID_POINT) return bad;
+        ctx_.check(rc);
+        return std::nullopt;
+    }
+    void append_uniform(const uint8_t* bytes64, size_t n) { ctx_.check(zk_table_append_uniform(ctx_.raw(), h_, bytes64, n)); }
+    std::vector<CompressedRistretto> compress(size_t offset, size_t n) const {
+        std::vector<CompressedRistretto> out(n);
+        ctx_.check(zk_table_compress(ctx_.raw(), h_, offset, n, reinterpret_cast<uint8_t*>(out.data())));
+        return out;
+    }
+    const zk_table* raw() const { return h_; }
+  private:
+    Context& ctx_;
+    zk_table* h_ = nullptr;
+};
+
+struct RistrettoPoint {
+    // sum scalars[i] * table[offset + i]
+    static CompressedRistretto vartime_multiscalar_mul(Context& ctx, const std::vector<Scalar>& scalars, const PointTable& points,
+                                                       size_t offset = 0) {
+        CompressedRistretto out{};
+        ctx.check(zk_msm_vartime_table(ctx.raw(), reinterpret_cast<const uint8_t*>(scalars.data()), points.raw(), offset,
+                                       scalars.size(), out.data()));
+        return out;
+    }
+    // sum scalars[i] * decompress(points[i]); nullopt if any encoding is invalid
+    static std::optional<CompressedRistretto> optional_multiscalar_mul(Context& ctx, const std::vector<Scalar>& scalars,
+                                                                       const std::vector<CompressedRistretto>& points) {
+        if (scalars.size() != points.size()) throw Error(ZK_ERR_ARG, "scalars/points length mismatch");
+        CompressedRistretto out{};
+        int rc = zk_msm_vartime(ctx.raw(), reinterpret_cast<const uint8_t*>(scalars.data()),
+                                reinterpret_cast<const uint8_t*>(points.data()), scalars.size(), out.data());
+        if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
+        ctx.check(rc);
+        return out;
+    }
+    static bool is_identity(const CompressedRistretto& c) { return zk_encoding_is_identity(c.data()) != 0; }
+};
+
+}  // namespace zkvm_b200
