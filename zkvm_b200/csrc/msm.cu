@@ -30,6 +30,7 @@ namespace {
 
 constexpr int REDUCE_RADIX_LOG2 = 3;               // tree fan-in 8
 constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
+constexpr uint32_t TASK_LEN = 64;                   // longest run of entries one accumulation thread walks
 
 __device__ __forceinline__ void ld_fe(fe& r, const uint4* p) {
     uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -182,78 +183,137 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     }
 }
 
-// ---- exclusive scan over the bucket counts (3 phases, 1024-element tiles) ---------------------
+// ---- scan + task planning (3 phases, 1024-bucket tiles) -----------------------------------------
+// Besides the exclusive scan of the bucket counts (-> offsets into `entries`), the same three passes split
+// every bucket into tasks of at most TASK_LEN entries and emit the task list SORTED BY LENGTH (longest
+// first).  One thread later runs one task, so the 32 lanes of a warp walk runs of (almost) equal length and
+// the grid's tail is made of the shortest tasks: the bucket-size distribution (Poisson per window, 8x heavier
+// in the top window, arbitrary for adversarial scalars) no longer decides the kernel's efficiency.
+//   scanned value (packed u64): lo = entries in the bucket, hi = tasks of the bucket
+//   bins[len], len in 1..TASK_LEN: number of tasks of that length; cursor = exclusive scan, descending length
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+__device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long long v) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += t; }
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
     return v;
 }
-// exclusive scan of one value per thread across a 256-thread block; returns the exclusive prefix, *total = block sum
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t wsum[8];
-    uint32_t inc = warp_incl_scan(v);
+// exclusive scan of one u64 per thread across a 256-thread block; *total = block sum
+__device__ __forceinline__ unsigned long long block_excl_scan_256(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long wsum[8];
+    unsigned long long inc = warp_incl_scan64(v);
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
-    uint32_t off = 0, tot = 0;
+    unsigned long long off = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { uint32_t x = wsum[k]; if (k < wid) off += x; tot += x; }
+    for (int k = 0; k < 8; k++) { unsigned long long x = wsum[k]; if (k < wid) off += x; tot += x; }
     *total = tot;
     __syncthreads();
     return off + inc - v;
 }
-
-__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ counts, size_t nb, uint32_t* __restrict__ tile_sums) {
-    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (base + k < nb) v += counts[base + k];
-    uint32_t tot; block_excl_scan_256(v, &tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+__device__ __forceinline__ unsigned long long pack_count(uint32_t cnt) {
+    return (unsigned long long)cnt | ((unsigned long long)((cnt + TASK_LEN - 1) / TASK_LEN) << 32);
 }
-__global__ void __launch_bounds__(256) k_scan_tiles(uint32_t* __restrict__ tile_sums, size_t ntiles) {
-    // single block; ntiles <= 256*8
-    __shared__ uint32_t carry_s;
+
+// plan[0] = total tasks, plan[1 + len] = bins (phase 1) / cursors (phase 2 on), len = 0..TASK_LEN
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ counts, size_t nb,
+                                                        unsigned long long* __restrict__ tile_sums, uint32_t* __restrict__ plan) {
+    __shared__ uint32_t s_bins[TASK_LEN + 1];
+    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_bins[i] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < nb) {
+            uint32_t cnt = counts[base + k];
+            v += pack_count(cnt);
+            uint32_t nfull = cnt / TASK_LEN, rem = cnt % TASK_LEN;
+            if (nfull) atomicAdd(&s_bins[TASK_LEN], nfull);
+            if (rem) atomicAdd(&s_bins[rem], 1u);
+        }
+    }
+    unsigned long long tot; block_excl_scan_256(v, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) if (s_bins[i]) atomicAdd(&plan[1 + i], s_bins[i]);
+}
+__global__ void __launch_bounds__(256) k_scan_tiles(unsigned long long* __restrict__ tile_sums, size_t ntiles, uint32_t* __restrict__ plan) {
+    // single block
+    __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     for (size_t base = 0; base < ntiles; base += 256) {
         size_t i = base + threadIdx.x;
-        uint32_t v = i < ntiles ? tile_sums[i] : 0u, tot;
-        uint32_t ex = block_excl_scan_256(v, &tot);
-        uint32_t cb = carry_s;
+        unsigned long long v = i < ntiles ? tile_sums[i] : 0ull, tot;
+        unsigned long long ex = block_excl_scan_256(v, &tot);
+        unsigned long long cb = carry_s;
         if (i < ntiles) tile_sums[i] = cb + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry_s = cb + tot;
         __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int len = TASK_LEN; len >= 1; len--) { uint32_t c = plan[1 + len]; plan[1 + len] = run; run += c; }
+        plan[0] = run;
+    }
 }
-__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ counts, size_t nb, const uint32_t* __restrict__ tile_offs,
-                                                    uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+// writes offsets/cursor (entry positions), task_off (first partial slot of each bucket) and the sorted task list
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ counts, size_t nb,
+                                                    const unsigned long long* __restrict__ tile_offs, uint32_t* __restrict__ offsets,
+                                                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_off,
+                                                    uint32_t* __restrict__ plan, uint2* __restrict__ tasks) {
+    __shared__ uint32_t s_bins[TASK_LEN + 1];
+    __shared__ uint32_t s_base[TASK_LEN + 1];
+    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_bins[i] = 0;
+    __syncthreads();
     size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = base + k < nb ? counts[base + k] : 0u; sum += v[k]; }
-    uint32_t tot;
-    uint32_t ex = block_excl_scan_256(sum, &tot) + tile_offs[blockIdx.x];
+    uint32_t cnt[4], r_full[4], r_rem[4];
+    unsigned long long sum = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (base + k < nb) { offsets[base + k] = ex; cursor[base + k] = ex; }
-        ex += v[k];
-        if (base + k == nb - 1) offsets[nb] = ex;
+        cnt[k] = base + k < nb ? counts[base + k] : 0u;
+        sum += pack_count(cnt[k]);
+        uint32_t nfull = cnt[k] / TASK_LEN, rem = cnt[k] % TASK_LEN;
+        r_full[k] = nfull ? atomicAdd(&s_bins[TASK_LEN], nfull) : 0u;
+        r_rem[k] = rem ? atomicAdd(&s_bins[rem], 1u) : 0u;
+    }
+    unsigned long long tot;
+    unsigned long long ex = block_excl_scan_256(sum, &tot) + tile_offs[blockIdx.x];   // has a __syncthreads
+    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_base[i] = s_bins[i] ? atomicAdd(&plan[1 + i], s_bins[i]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < nb) {
+            uint32_t b = (uint32_t)(base + k);
+            offsets[b] = (uint32_t)ex; cursor[b] = (uint32_t)ex; task_off[b] = (uint32_t)(ex >> 32);
+            uint32_t nfull = cnt[k] / TASK_LEN, rem = cnt[k] % TASK_LEN;
+            uint32_t p = s_base[TASK_LEN] + r_full[k];
+            for (uint32_t j = 0; j < nfull; j++) tasks[p + j] = make_uint2(b, j);
+            if (rem) tasks[s_base[rem] + r_rem[k]] = make_uint2(b, nfull);
+        }
+        ex += pack_count(cnt[k]);
+        if (base + k == nb - 1) { offsets[nb] = (uint32_t)ex; task_off[nb] = (uint32_t)(ex >> 32); }
     }
 }
 
 // ---- bucket accumulation ------------------------------------------------------------------------
 
-// One thread per (window, bucket).  entries[offsets[t] .. offsets[t+1]) are the indices (bit 31 = subtract) of
-// the points whose digit in this window has magnitude bucket+1.  Index space: [0, split) -> tab_a, the rest -> tab_b.
+// One thread per task = up to TASK_LEN consecutive entries of one bucket's sorted run.  An entry is a point index
+// (bit 31 = subtract); index space [0, split) -> tab_a, the rest -> tab_b.  The partial sum goes to
+// partials[task_off[bucket] + j]; the tree's leaf level adds a bucket's partials together.
 __global__ void __launch_bounds__(128) k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split,
                                                       const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
-                                                      size_t nbuckets, uint4* __restrict__ buckets) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbuckets) return;
-    uint32_t lo = offsets[t], hi = offsets[t + 1];
+                                                      const uint32_t* __restrict__ task_off, const uint2* __restrict__ tasks,
+                                                      const uint32_t* __restrict__ plan, uint4* __restrict__ partials) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plan[0]) return;
+    uint2 d = tasks[t];
+    uint32_t lo = offsets[d.x] + d.y * TASK_LEN, end = offsets[d.x + 1];
+    uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
     ge_ext acc; ge_identity(acc);
 #pragma unroll 1
     for (uint32_t k = lo; k < hi; k++) {
@@ -263,32 +323,89 @@ __global__ void __launch_bounds__(128) k_bucket_accum(const uint4* __restrict__ 
         if (idx < split) ld_niels(q, tab_a, idx); else ld_niels(q, tab_b, idx - split);
         ge_madd(acc, acc, q, (e >> 31) != 0);
     }
-    st_ext(buckets, t, acc);
+    st_ext(partials, task_off[d.x] + d.y, acc);
 }
 
 // ---- radix-8 reduction tree ---------------------------------------------------------------------
 // A node covering children i = 0..L-1 (each of width `wc` buckets) combines
 //     A  = sum_i A_i                       (plain sum)
 //     Wt = sum_i Wt_i + wc * sum_i i*A_i   (sum weighted by 1-based position inside the node)
-// At the leaves A_i = Wt_i = bucket i (wc = 1).  The root's Wt is the window sum  sum_b (b+1) * S_b.
-__global__ void __launch_bounds__(128) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in, size_t m_in,
+// At the leaves A_i = Wt_i = bucket i (wc = 1), and bucket i is itself the sum of its tasks' partials
+// (none for an empty bucket).  The root's Wt is the window sum  sum_b (b+1) * S_b.
+__device__ __forceinline__ void ge_shfl_xor(ge_ext& r, const ge_ext& p, int mask) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.v[i] = __shfl_xor_sync(0xffffffffu, p.X.v[i], mask);
+        r.Y.v[i] = __shfl_xor_sync(0xffffffffu, p.Y.v[i], mask);
+        r.Z.v[i] = __shfl_xor_sync(0xffffffffu, p.Z.v[i], mask);
+        r.T.v[i] = __shfl_xor_sync(0xffffffffu, p.T.v[i], mask);
+    }
+}
+constexpr uint32_t HEAVY_PARTIALS = 32;   // a bucket with more partials than this is summed by the whole warp
+
+// Leaf-level child = bucket `idx`: the sum of its tasks' partials (identity when it has none).  Must be called by
+// all 32 lanes (valid = false for lanes without a child): a bucket that was split into many tasks -- adversarial
+// scalars put up to n / TASK_LEN partials in ONE bucket -- is reduced by the warp together: strided partial
+// sums, then a shuffle butterfly.
+__device__ __forceinline__ void load_bucket(ge_ext& r, const uint4* __restrict__ partials, const uint32_t* __restrict__ task_off,
+                                            size_t idx, bool valid) {
+    uint32_t p0 = 0, p1 = 0;
+    if (valid) { p0 = task_off[idx]; p1 = task_off[idx + 1]; }
+    bool heavy = p1 - p0 > HEAVY_PARTIALS;
+    unsigned hmask = __ballot_sync(0xffffffffu, heavy);
+    ge_ext tmp;
+    if (!heavy) {
+        if (p0 == p1) ge_identity(r);
+        else {
+            ld_ext(r, partials, p0);
+#pragma unroll 1
+            for (uint32_t p = p0 + 1; p < p1; p++) { ld_ext(tmp, partials, p); ge_add(r, r, tmp); }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    while (hmask) {
+        int src = __ffs(hmask) - 1; hmask &= hmask - 1;
+        uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+        ge_ext part; ge_identity(part);
+#pragma unroll 1
+        for (uint32_t p = q0 + lane; p < q1; p += 32) { ld_ext(tmp, partials, p); ge_add(part, part, tmp); }
+#pragma unroll 1
+        for (int o = 16; o >= 1; o >>= 1) { ge_shfl_xor(tmp, part, o); ge_add(part, part, tmp); }
+        if (lane == src) r = part;
+    }
+}
+__global__ void __launch_bounds__(128) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in,
+                                                    const uint32_t* __restrict__ task_off, size_t m_in,
                                                     size_t m_out, int windows, int log2_wc,
                                                     uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m_out * (size_t)windows) return;
-    size_t w = t / m_out, k = t % m_out;
+    const bool active = t < m_out * (size_t)windows;      // inactive lanes still take part in the warp-wide leaf loads
+    size_t w = active ? t / m_out : 0, k = active ? t % m_out : 0;
     size_t first = k * REDUCE_RADIX, last = first + REDUCE_RADIX;
     if (last > m_in) last = m_in;
-    const uint4* ain = a_in + w * m_in * 8;
+    if (!active) last = first;
     ge_ext run, acc, wsum, tmp;
     ge_identity(run); ge_identity(acc); ge_identity(wsum);
     // top-down running sum: after the loop run = sum A_i, acc = sum (i+1) A_i
+    if (task_off != nullptr) {
+        // leaf level: children are global bucket ids w*m_in + j, looked up through task_off
 #pragma unroll 1
-    for (size_t j = last; j-- > first;) {
-        ld_ext(tmp, ain, j);
-        ge_add(run, run, tmp);
-        ge_add(acc, acc, run);
+        for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
+            size_t j = first + jj;
+            bool valid = j < last;
+            load_bucket(tmp, a_in, task_off, w * m_in + j, valid);
+            if (valid) { ge_add(run, run, tmp); ge_add(acc, acc, run); }
+        }
+    } else {
+        const uint4* ain = a_in + w * m_in * 8;
+#pragma unroll 1
+        for (size_t j = last; j-- > first;) {
+            ld_ext(tmp, ain, j);
+            ge_add(run, run, tmp);
+            ge_add(acc, acc, run);
+        }
     }
+    if (!active) return;
     if (wt_in != nullptr) {
         // acc - run = sum i*A_i ; scale by wc, add the children's weighted sums
         ge_neg(tmp, run); ge_add(acc, acc, tmp);
@@ -408,7 +525,7 @@ struct zk_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
     // workspace
-    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, buckets, tree_a, tree_w, out_ext, out32, bad;
+    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, partials, task_off, tasks, plan, tree_a, tree_w, out_ext, out32, bad;
     uint8_t* h_out = nullptr;               // pinned 64 B: [0,32) encoding, [32,40) bad index
 };
 
@@ -484,7 +601,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->scalars, &ctx->comp, &ctx->dyn_table, &ctx->counts, &ctx->cursor, &ctx->offsets, &ctx->tiles,
-                      &ctx->entries, &ctx->buckets, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad};
+                      &ctx->entries, &ctx->partials, &ctx->task_off, &ctx->tasks, &ctx->plan, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -651,48 +768,60 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
     const size_t NB = B * W;
     const size_t ntiles = (NB + 1023) / 1024;
 
+    if ((unsigned long long)n * W >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
+    const size_t max_tasks = NB + (n * (size_t)W) / TASK_LEN;
     TRY(ensure(ctx, ctx->counts, NB * 4));
     TRY(ensure(ctx, ctx->cursor, NB * 4));
     TRY(ensure(ctx, ctx->offsets, (NB + 1) * 4));
-    TRY(ensure(ctx, ctx->tiles, ntiles * 4));
+    TRY(ensure(ctx, ctx->task_off, (NB + 1) * 4));
+    TRY(ensure(ctx, ctx->tiles, ntiles * 8));
+    TRY(ensure(ctx, ctx->plan, (TASK_LEN + 2) * 4));
+    TRY(ensure(ctx, ctx->tasks, max_tasks * 8));
     TRY(ensure(ctx, ctx->entries, n * W * 4));
-    TRY(ensure(ctx, ctx->buckets, NB * 128));
+    TRY(ensure(ctx, ctx->partials, max_tasks * 128));
     size_t m1 = (B + REDUCE_RADIX - 1) / REDUCE_RADIX;
     TRY(ensure(ctx, ctx->tree_a, 2 * m1 * W * 128));     // ping-pong halves
     TRY(ensure(ctx, ctx->tree_w, 2 * m1 * W * 128));
 
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
+    CK(ctx, cudaMemsetAsync(ctx->plan.p, 0, (TASK_LEN + 2) * 4, st));
     k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->counts.p);
     LAUNCH_CHECK(ctx);
-    k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (uint32_t*)ctx->tiles.p);
+    k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (unsigned long long*)ctx->tiles.p,
+                                                        (uint32_t*)ctx->plan.p);
     LAUNCH_CHECK(ctx);
-    k_scan_tiles<<<1, 256, 0, st>>>((uint32_t*)ctx->tiles.p, ntiles);
+    k_scan_tiles<<<1, 256, 0, st>>>((unsigned long long*)ctx->tiles.p, ntiles, (uint32_t*)ctx->plan.p);
     LAUNCH_CHECK(ctx);
-    k_scan_apply<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (const uint32_t*)ctx->tiles.p,
-                                                    (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p);
+    k_scan_apply<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (const unsigned long long*)ctx->tiles.p,
+                                                    (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->task_off.p,
+                                                    (uint32_t*)ctx->plan.p, (uint2*)ctx->tasks.p);
     LAUNCH_CHECK(ctx);
     k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->cursor.p,
                                                        (uint32_t*)ctx->entries.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
 
-    k_bucket_accum<<<grid_for(NB, 128), 128, 0, st>>>(tab_a, tab_b, (uint32_t)split, (const uint32_t*)ctx->entries.p,
-                                                       (const uint32_t*)ctx->offsets.p, NB, (uint4*)ctx->buckets.p);
+    // grid sized for the worst case; threads past the device-side task count exit at once
+    k_bucket_accum<<<grid_for(max_tasks, 128), 128, 0, st>>>(tab_a, tab_b, (uint32_t)split, (const uint32_t*)ctx->entries.p,
+                                                              (const uint32_t*)ctx->offsets.p, (const uint32_t*)ctx->task_off.p,
+                                                              (const uint2*)ctx->tasks.p, (const uint32_t*)ctx->plan.p,
+                                                              (uint4*)ctx->partials.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[3], st));
 
     // radix-8 tree, per window, until one node is left
-    const uint4* a_in = (const uint4*)ctx->buckets.p;
+    const uint4* a_in = (const uint4*)ctx->partials.p;
     const uint4* w_in = nullptr;
+    const uint32_t* toff = (const uint32_t*)ctx->task_off.p;
     size_t m_in = B; int log2_wc = 0; int half = 0;
     while (true) {
         size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
-        k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, W, log2_wc, a_out, w_out);
+        k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
-        a_in = a_out; w_in = w_out; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
+        a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
     }
     k_window_combine<<<1, 32, 0, st>>>(w_in, W, c, (uint4*)out_ext_dev);
