@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkmsm.so")
+# ZKMSM_LIB: developer override used by tools/perf_variants.sh to A/B kernel builds; the default is the in-tree library
+LIB_PATH = os.environ.get("ZKMSM_LIB") or os.path.join(_HERE, "libzkmsm.so")
 
 ZK_OK, ZK_ERR_CUDA, ZK_ERR_INVALID_POINT, ZK_ERR_ARG, ZK_ERR_NOMEM = 0, -1, -2, -3, -4
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void st_ext(uint4* base, size_t idx, const ge_ext& r)
 
 // RFC 9496 4.3.1 over a batch; writes affine-Niels entries.  *bad = lowest rejected index.
 __global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
-                                                    unsigned long long* __restrict__ bad) {
+                                                    unsigned long long* __restrict__ bad, unsigned long long index_base) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in
     fe x, y, t;
     bool ok = ristretto_decode(x, y, t, w);
     ge_niels q;
-    if (ok) ge_to_niels_affine(q, x, y, t); else { ge_niels_identity(q); atomicMin(bad, (unsigned long long)i); }
+    if (ok) ge_to_niels_affine(q, x, y, t); else { ge_niels_identity(q); atomicMin(bad, index_base + (unsigned long long)i); }
     st_niels(table, i, q);
 }
 
@@ -305,24 +305,48 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
 // One thread per task = up to TASK_LEN consecutive entries of one bucket's sorted run.  An entry is a point index
 // (bit 31 = subtract); index space [0, split) -> tab_a, the rest -> tab_b.  The partial sum goes to
 // partials[task_off[bucket] + j]; the tree's leaf level adds a bucket's partials together.
-__global__ void __launch_bounds__(128) k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split,
-                                                      const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
-                                                      const uint32_t* __restrict__ task_off, const uint2* __restrict__ tasks,
-                                                      const uint32_t* __restrict__ plan, uint4* __restrict__ partials) {
+#ifndef ZK_ACCUM_MINBLOCKS
+#define ZK_ACCUM_MINBLOCKS 3
+#endif
+#ifndef ZK_ACCUM_PREFETCH
+#define ZK_ACCUM_PREFETCH 0
+#endif
+__device__ __forceinline__ void ld_point(ge_niels& q, const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split, uint32_t e) {
+    uint32_t idx = e & 0x7fffffffu;
+    if (idx < split) ld_niels(q, tab_a, idx); else ld_niels(q, tab_b, idx - split);
+}
+__global__ void __launch_bounds__(128, ZK_ACCUM_MINBLOCKS)
+k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split,
+               const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+               const uint32_t* __restrict__ task_off, const uint2* __restrict__ tasks,
+               const uint32_t* __restrict__ plan, uint4* __restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= plan[0]) return;
     uint2 d = tasks[t];
     uint32_t lo = offsets[d.x] + d.y * TASK_LEN, end = offsets[d.x + 1];
     uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
     ge_ext acc; ge_identity(acc);
+#if ZK_ACCUM_PREFETCH
+    // software pipeline: the index two entries ahead and the point one entry ahead are in flight during a madd
+    uint32_t e0 = entries[lo];                       // a task is never empty
+    uint32_t e1 = lo + 1 < hi ? entries[lo + 1] : 0u;
+    ge_niels q; ld_point(q, tab_a, tab_b, split, e0);
+#pragma unroll 1
+    for (uint32_t k = lo; k < hi; k++) {
+        uint32_t e2 = k + 2 < hi ? entries[k + 2] : 0u;
+        ge_niels qn;
+        if (k + 1 < hi) ld_point(qn, tab_a, tab_b, split, e1); else qn = q;
+        ge_madd(acc, acc, q, (e0 >> 31) != 0);
+        q = qn; e0 = e1; e1 = e2;
+    }
+#else
 #pragma unroll 1
     for (uint32_t k = lo; k < hi; k++) {
         uint32_t e = entries[k];
-        uint32_t idx = e & 0x7fffffffu;
-        ge_niels q;
-        if (idx < split) ld_niels(q, tab_a, idx); else ld_niels(q, tab_b, idx - split);
+        ge_niels q; ld_point(q, tab_a, tab_b, split, e);
         ge_madd(acc, acc, q, (e >> 31) != 0);
     }
+#endif
     st_ext(partials, task_off[d.x] + d.y, acc);
 }
 
@@ -374,7 +398,10 @@ __device__ __forceinline__ void load_bucket(ge_ext& r, const uint4* __restrict__
         if (lane == src) r = part;
     }
 }
-__global__ void __launch_bounds__(128) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in,
+#ifndef ZK_LEAF_MINBLOCKS
+#define ZK_LEAF_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, ZK_LEAF_MINBLOCKS) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in,
                                                     const uint32_t* __restrict__ task_off, size_t m_in,
                                                     size_t m_out, int windows, int log2_wc,
                                                     uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
@@ -420,19 +447,119 @@ __global__ void __launch_bounds__(128) k_tree_level(const uint4* __restrict__ a_
     st_ext(wt_out, t, acc);
 }
 
-// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  Single thread (253 dependent doublings).
-__global__ void k_window_combine(const uint4* __restrict__ wt, int windows, int c, uint4* __restrict__ out_ext) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    ge_ext acc, tmp;
-    ld_ext(acc, wt, windows - 1);
+// ---- 4-lane cooperative point arithmetic ("quads") ----------------------------------------------
+// The upper tree levels and the window Horner are chains of dependent point operations with almost no
+// parallelism across threads, so their cost is the latency of one operation.  A quad = 4 adjacent lanes holding
+// one extended point, lane q owning one coordinate (0:X 1:Y 2:Z 3:T).  The 4 independent field multiplies of each
+// half of the HWCD formulas run in the 4 lanes at once (the layout dalek's AVX2 backend uses across vector lanes);
+// operands move between lanes with warp shuffles.  Depth per addition: 3 multiplies instead of 9; per doubling:
+// 1 squaring + 1 multiply instead of 4 + 4.  Every lane of the warp must execute these calls (full-mask shuffles):
+// roles are chosen with selects, never with branches.
+__device__ __forceinline__ void fe_shfl(fe& r, const fe& a, int src) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+}
+__device__ __forceinline__ void fe_shfl_xor(fe& r, const fe& a, int m) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], m);
+}
+__device__ __forceinline__ void quad_identity(fe& r, int q) { r = fe_zero(); r.v[0] = (q == 1 || q == 2) ? 1u : 0u; }
+// in: lane0 = E, lane1 = H, lane2 = F, lane3 = G.  out: (X3, Y3, Z3, T3) = (E*F, G*H, F*G, E*H) in lanes 0..3.
+__device__ __forceinline__ void quad_finish(fe& r, const fe& val, int q, int base) {
+    fe m1, m2, x;
+    fe_shfl(m1, val, base + (q == 0 ? 2 : (q == 3 ? 0 : 3)));
+    fe_shfl(m2, val, base + 1);
+    fe_select(x, val, m2, q == 3);
+    fe_mul(r, x, m1);
+}
+// r = p + qq (both in quad layout).  Unified a = -1 addition, complete.
+__device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, int q, int base) {
+    const bool l0 = q == 0, hi = q >= 2;
+    fe op, oq, a, b, dif, sum, u, v;
+    fe_shfl_xor(op, p, 1); fe_shfl_xor(oq, qq, 1);
+    fe_select(a, p, op, l0); fe_select(b, op, p, l0);          // lanes 0/1: a = Y1, b = X1
+    fe_sub(dif, a, b); fe_add(sum, a, b);
+    fe_select(u, sum, dif, l0); fe_select(u, u, p, hi);         // Y1-X1 | Y1+X1 | Z1 | T1
+    fe_select(a, qq, oq, l0); fe_select(b, oq, qq, l0);
+    fe_sub(dif, a, b); fe_add(sum, a, b);
+    fe_select(v, sum, dif, l0); fe_select(v, v, qq, hi);        // Y2-X2 | Y2+X2 | Z2 | T2
+    fe k = fe_d2();
+#pragma unroll
+    for (int i = 0; i < 8; i++) k.v[i] = q == 3 ? k.v[i] : (i == 0 ? (q == 2 ? 2u : 1u) : 0u);
+    fe_mul(v, v, k);                                            // ... | ... | 2 Z2 | 2d T2
+    fe r1, o;
+    fe_mul(r1, u, v);                                           // A | B | D | C
+    fe_shfl_xor(o, r1, 1);
+    fe_add(sum, r1, o);
+    fe_select(a, r1, o, l0); fe_select(b, o, r1, l0);
+    fe_sub(dif, a, b);                                          // lane0: B-A = E, lane2: D-C = F
+    fe val; fe_select(val, dif, sum, (q & 1) != 0);             // lane1: B+A = H, lane3: D+C = G
+    quad_finish(r, val, q, base);
+}
+// r = 2p.
+__device__ __forceinline__ void quad_dbl(fe& r, const fe& p, int q, int base) {
+    fe x0, y0, s, opnd, sq, A, Bv, t, apb, bma, c2, L, R, val, z = fe_zero();
+    fe_shfl(x0, p, base); fe_shfl(y0, p, base + 1);
+    fe_add(s, x0, y0);
+    fe_select(opnd, p, s, q == 3);
+    fe_sqr(sq, opnd);                                           // X^2 | Y^2 | Z^2 | (X+Y)^2
+    fe_shfl(A, sq, base); fe_shfl(Bv, sq, base + 1); fe_shfl(t, sq, base + 3);
+    fe_add(apb, A, Bv); fe_sub(bma, Bv, A); fe_add(c2, sq, sq);
+    fe_select(L, bma, t, q == 0); fe_select(L, L, z, q == 1);    // t | 0 | B-A | B-A
+    fe_select(R, apb, c2, q == 2); fe_select(R, R, z, q == 3);   // A+B | A+B | 2Z^2 | 0
+    fe_sub(val, L, R);                                          // E | H | F | G
+    quad_finish(r, val, q, base);
+}
+__device__ __forceinline__ void quad_neg(fe& r, const fe& p, int q) { fe_cneg(r, p, q == 0 || q == 3); }
+__device__ __forceinline__ void quad_ld(fe& r, const uint4* base, size_t idx, int q) { ld_fe_plain(r, base + idx * 8 + q * 2); }
+__device__ __forceinline__ void quad_st(uint4* base, size_t idx, int q, const fe& r) { st_fe(base + idx * 8 + q * 2, r); }
+
+// Upper tree levels: one quad per node (see k_tree_level for the recurrence).  Trip counts are warp-uniform;
+// missing children are the identity.
+__global__ void __launch_bounds__(128) k_tree_level_quad(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in, size_t m_in,
+                                                         size_t m_out, int windows, int log2_wc,
+                                                         uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
+    size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    size_t t = gt >> 2;
+    const bool active = t < m_out * (size_t)windows;
+    size_t w = active ? t / m_out : 0, k = active ? t % m_out : 0;
+    size_t first = k * REDUCE_RADIX;
+    const uint4* ain = a_in + w * m_in * 8;
+    const uint4* win = wt_in + w * m_in * 8;
+    fe run, acc, wsum, tmp;
+    quad_identity(run, q); quad_identity(acc, q); quad_identity(wsum, q);
+#pragma unroll 1
+    for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
+        size_t j = first + jj;
+        bool valid = active && j < m_in;
+        if (valid) quad_ld(tmp, ain, j, q); else quad_identity(tmp, q);
+        quad_add(run, run, tmp, q, base);
+        quad_add(acc, acc, run, q, base);
+        if (valid) quad_ld(tmp, win, j, q); else quad_identity(tmp, q);
+        quad_add(wsum, wsum, tmp, q, base);
+    }
+    quad_neg(tmp, run, q); quad_add(acc, acc, tmp, q, base);      // sum i*A_i
+#pragma unroll 1
+    for (int d = 0; d < log2_wc; d++) quad_dbl(acc, acc, q, base);
+    quad_add(acc, acc, wsum, q, base);
+    if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
+}
+
+// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  One warp; every quad computes the same chain
+// (253 dependent doublings), quad 0 stores.
+__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int c, uint4* __restrict__ out_ext) {
+    const int q = threadIdx.x & 3, base = threadIdx.x & ~3;
+    fe acc, tmp;
+    quad_ld(acc, wt, windows - 1, q);
 #pragma unroll 1
     for (int w = windows - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (int d = 0; d < c; d++) ge_dbl(acc, acc);
-        ld_ext(tmp, wt, w);
-        ge_add(acc, acc, tmp);
+        for (int d = 0; d < c; d++) quad_dbl(acc, acc, q, base);
+        quad_ld(tmp, wt, w, q);
+        quad_add(acc, acc, tmp, q, base);
     }
-    st_ext(out_ext, 0, acc);
+    if (threadIdx.x < 4) quad_st(out_ext, 0, q, acc);
 }
 
 __global__ void k_set_identity(uint4* __restrict__ out_ext) {
@@ -523,6 +650,11 @@ struct zk_ctx {
     int profiling = 0;
     float phase_ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // copy/decode side streams: compressed points are uploaded and decoded in chunks on these two while the
+    // main stream uploads the scalars and sorts digits; the main stream joins them right before the accumulation
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool join_aux = false;
     uint64_t launches = 0;
     // workspace
     DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, partials, task_off, tasks, plan, tree_a, tree_w, out_ext, out32, bad;
@@ -585,6 +717,9 @@ extern "C" int zk_ctx_create(int device, zk_ctx** out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_out, 64);
     if (e != cudaSuccess) {
         fprintf(stderr, "zkmsm: cannot create context on CUDA device %d: %s (there is no CPU fallback)\n", device,
@@ -605,6 +740,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (int i = 0; i < 2; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -688,7 +825,7 @@ static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* ta
     TRY(ensure(ctx, ctx->bad, 8));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
     k_decompress<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
-                                                             (unsigned long long*)ctx->bad.p);
+                                                             (unsigned long long*)ctx->bad.p, 0ull);
     LAUNCH_CHECK(ctx);
     if (!sync) return ZK_OK;
     CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -802,6 +939,10 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
 
+    if (ctx->join_aux) {          // the point table is being produced on the side streams
+        for (int i = 0; i < 2; i++) CK(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+        ctx->join_aux = false;
+    }
     // grid sized for the worst case; threads past the device-side task count exit at once
     k_bucket_accum<<<grid_for(max_tasks, 128), 128, 0, st>>>(tab_a, tab_b, (uint32_t)split, (const uint32_t*)ctx->entries.p,
                                                               (const uint32_t*)ctx->offsets.p, (const uint32_t*)ctx->task_off.p,
@@ -819,7 +960,10 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
-        k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
+        if (w_in == nullptr)
+            k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
+        else
+            k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
@@ -887,18 +1031,32 @@ extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32
     TRY(ensure(ctx, ctx->dyn_table, n_dyn * 96));
     TRY(ensure(ctx, ctx->bad, 8));
     cudaStream_t st = ctx->stream;
-    if (n_static) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_static32_host, n_static * 32, cudaMemcpyHostToDevice, st));
-    if (n_dyn) {
-        CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
-        CK(ctx, cudaMemcpyAsync(ctx->comp.p, points_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
-    }
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], st));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
-    TRY(decompress_into(ctx, ctx->comp.p, n_dyn, (uint4*)ctx->dyn_table.p, 0, nullptr, false));
-    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));
+    if (n_dyn) {
+        // upload + decode the points in chunks, alternating between the two side streams so that the copy of
+        // chunk i+1 overlaps the decode of chunk i; the scalars go up on the main stream behind them
+        CK(ctx, cudaEventRecord(ctx->ev_fork, st));
+        const size_t chunk = n_dyn > (1u << 16) ? (n_dyn + 7) / 8 : n_dyn;
+        int which = 0;
+        for (size_t lo = 0; lo < n_dyn; lo += chunk, which ^= 1) {
+            size_t cnt = n_dyn - lo < chunk ? n_dyn - lo : chunk;
+            cudaStream_t sa = ctx->aux[which];
+            if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+            CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->comp.p + lo * 32, points_dyn32_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sa));
+            k_decompress<<<grid_for(cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
+                                                            (unsigned long long*)ctx->bad.p, (unsigned long long)lo);
+            LAUNCH_CHECK(ctx);
+        }
+        for (int i = 0; i < 2; i++) CK(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+        ctx->join_aux = true;
+    }
+    if (n_static) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_static32_host, n_static * 32, cudaMemcpyHostToDevice, st));
+    if (n_dyn) CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
     TRY(msm_pipeline(ctx, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, n, ctx->out_ext.p));
     if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], st));
+    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));    // after the join inside the pipeline
     TRY(finish_encode(ctx, ctx->out_ext.p, 1, out32));
     unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
     if (n_dyn && b != ~0ull) { memset(out32, 0, 32); return ZK_ERR_INVALID_POINT; }
