@@ -32,17 +32,22 @@ LOG2_N = 20
 METRIC = "ristretto255_vartime_msm_points_per_s"
 UNIT = "points/s"
 MAC_PER_FE_MUL = 72      # 64 limb products + 8 for the 2^256 = 38 fold
+# dram__bytes_read.sum + dram__bytes_write.sum of k_bucket_accum at n = 2^20, c = 16 (profiles/r01_ncu_full_k_bucket_accum.txt)
+NCU_ACCUM_DRAM_BYTES = 1.176171e9 + 60.88832e6
 BLOCKED = "verified ZkVM tx/s: blocked, needs slingshot zkvm + bulletproofs + dalek sources (SURVEY.md section 0)"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="points per GPU (default 2^20, the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="MSMs in flight: each uses its own context (stream + workspace), so the serial tail of one step "
+                         "(Horner + encode, a few warps) overlaps the next step's accumulation; 1 = strictly serial")
     return ap.parse_args()
 
 
@@ -62,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
         except OSError:
             self.proc = None
@@ -166,8 +171,10 @@ def run_cuda(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = zk.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    F = max(1, a.inflight)
+    ctxs = [zk.Context(local) for _ in range(F)]
+    ctx = ctxs[0]
+    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
     n = 1 << a.log2n
     K, W = a.steps, max(a.warmup, 3)
 
@@ -190,29 +197,43 @@ def run_cuda(a):
         del c
     torch.cuda.synchronize()
 
-    part = torch.empty(PARTIAL_BYTES, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world, PARTIAL_BYTES, dtype=torch.uint8, device=dev)
+    parts = [torch.empty(PARTIAL_BYTES, dtype=torch.uint8, device=dev) for _ in range(F)]
+    gathered = [torch.empty(world, PARTIAL_BYTES, dtype=torch.uint8, device=dev) for _ in range(F)]
 
-    def step_device(i):
-        s = i % SETS
-        ctx.msm_table_dev(scal_dev[s].data_ptr(), tables[s], 0, n, part.data_ptr())
+    def submit(i):
+        """Queue step i on context i % F: the whole MSM pipeline, asynchronously, plus (N > 1) the one gather."""
+        f, s = i % F, i % SETS
+        ctxs[f].msm_table_dev(scal_dev[s].data_ptr(), tables[s], 0, n, parts[f].data_ptr())
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, part.view(1, PARTIAL_BYTES))
-            return ctx.ext_sum_compress_dev(gathered.data_ptr(), world) if rank == 0 else None
-        return ctx.ext_sum_compress_dev(part.data_ptr(), 1)
+            with torch.cuda.stream(streams[f]):
+                dist.all_gather_into_tensor(gathered[f], parts[f].view(1, PARTIAL_BYTES))
+
+    def collect(i):
+        """Finish step i: sum the partial(s), encode, read the 32 bytes back (synchronises that context only)."""
+        f = i % F
+        if world > 1:
+            return ctxs[f].ext_sum_compress_dev(gathered[f].data_ptr(), world) if rank == 0 else ctxs[f].sync()
+        return ctxs[f].ext_sum_compress_dev(parts[f].data_ptr(), 1)
+
+    def run_steps(k):
+        out = None
+        for i in range(k):
+            submit(i)
+            if i >= F - 1: out = collect(i - (F - 1))
+        for i in range(max(0, k - (F - 1)), k): out = collect(i)
+        return out
 
     np_scal = [t.numpy() for t in scal_host]; np_comp = [t.numpy() for t in comp_host]
 
     def step_e2e(i):
-        s = i % SETS
-        if world == 1:
-            return zk.RistrettoPoint.optional_multiscalar_mul(ctx, np_scal[s], np_comp[s])
-        # sharded: host buffers -> this rank's partial (decode + MSM on the device) -> gather -> rank 0 combines
-        r = zk.RistrettoPoint.optional_multiscalar_mul(ctx, np_scal[s], np_comp[s])
-        enc = torch.frombuffer(bytearray(bytes(r) + bytes(PARTIAL_BYTES - 32)), dtype=torch.uint8).to(dev)
-        dist.all_gather_into_tensor(gathered, enc.view(1, PARTIAL_BYTES))
-        torch.cuda.synchronize()
+        f, s = i % F, i % SETS
+        r = zk.RistrettoPoint.optional_multiscalar_mul(ctxs[f], np_scal[s], np_comp[s])
+        if world > 1:
+            # sharded: this rank's partial came back as 32 bytes; one gather, rank 0 would add the G encodings
+            enc = torch.frombuffer(bytearray(bytes(r) + bytes(PARTIAL_BYTES - 32)), dtype=torch.uint8).to(dev)
+            with torch.cuda.stream(streams[f]):
+                dist.all_gather_into_tensor(gathered[f], enc.view(1, PARTIAL_BYTES))
+            streams[f].synchronize()
         return r
 
     def barrier():
@@ -220,25 +241,37 @@ def run_cuda(a):
         torch.cuda.synchronize()
 
     # ---- parity gate before timing: device path == host-buffer path, bit for bit ----
-    r_dev = step_device(0)
+    r_dev = run_steps(1)
     r_e2e = zk.RistrettoPoint.optional_multiscalar_mul(ctx, np_scal[0], np_comp[0])
     if world == 1 and bytes(r_dev) != bytes(r_e2e):
         raise SystemExit("parity gate failed: table path and compressed path disagree")
 
-    # ---- `value`: inputs resident in HBM, CUDA events on the launching stream ----
-    for i in range(W): step_device(i)
+    # ---- `value`: inputs resident in HBM, CUDA events on the launching streams ----
+    run_steps(W)
     sampler = ClockSampler(local)
     if rank == 0: sampler.start()
     barrier()
-    launches0 = ctx.launch_count
+    launches0 = sum(c.launch_count for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K): step_device(i)
-    e1.record(stream)
+    cur = torch.cuda.current_stream(dev)
+    e0.record(cur)
+    for st in streams: st.wait_event(e0)
+    run_steps(K)
+    for st in streams: cur.wait_stream(st)
+    e1.record(cur)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(c.launch_count for c in ctxs) - launches0
+    # single-MSM latency (one context, strictly serial) for the record
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(streams[0])
+    for i in range(4):
+        ctx.msm_table_dev(scal_dev[i % SETS].data_ptr(), tables[i % SETS], 0, n, parts[0].data_ptr())
+        ctx.ext_sum_compress_dev(parts[0].data_ptr(), 1)
+    l1.record(streams[0])
+    barrier()
+    latency_ms = l0.elapsed_time(l1) / 4
 
     # ---- roofline of the dominant kernel (bucket accumulation), measured live with CUDA events ----
     ctx.set_profiling(True)
@@ -255,13 +288,26 @@ def run_cuda(a):
     imad_peak = ctx.bench_int_pipe(0)
     alg_bytes = adds * (96 + 4) + Wn * (1 << (c - 1)) * (128 + 8)
 
-    # ---- `e2e`: host buffers through the public API ----
-    for i in range(W): step_e2e(i)
+    # ---- `e2e`: host buffers through the public API; F host threads, one context each (ctypes drops the GIL) ----
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=F)
+
+    def run_e2e(k):
+        futs = [pool.submit(lambda f=f: [step_e2e(i) for i in range(f, k, F)]) for f in range(F)]
+        return [x.result() for x in futs]
+
+    run_e2e(W)
     barrier()
     t0 = time.perf_counter()
-    for i in range(K): step_e2e(i)
+    res = run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
+    if world == 1 and bytes(res[0][0]) != bytes(r_dev):
+        raise SystemExit("parity gate failed inside the e2e loop")
+    barrier(); t1 = time.perf_counter()
+    for i in range(3): step_e2e(i * F)
+    e2e_latency_ms = (time.perf_counter() - t1) / 3 * 1e3
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -278,22 +324,27 @@ def run_cuda(a):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (8 saturated 32-bit limbs, IMAD.WIDE)", "data": "synthetic",
             "config": {"workload": workload_name(a.log2n, world), "window_bits": c, "windows": Wn,
-                       "l2": "2 alternating resident input sets of 128 MiB each (> 126 MB L2); workspace 190 MiB",
+                       "l2": "2 alternating resident input sets of 128 MiB each (> 126 MB L2); workspace ~300 MiB per context",
+                       "inflight": F, "single_msm_latency_ms": latency_ms,
+                       "pipelining": f"{F} contexts (stream + workspace each) in flight; results are collected in order, one step behind",
                        "value_inputs": "scalars + cached decompressed points (affine Niels, 96 B) resident in HBM",
                        "parallelism": f"point-range shards x{world}, one 128 B all_gather per step" if world > 1 else "single GPU"},
             "e2e": {"value": n * world * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": 64 * n * world, "d2h_bytes_per_step": 40 * world,
+                    "h2d_bytes_per_step": 64 * n * world, "d2h_bytes_per_step": 40 * world, "single_call_latency_ms": e2e_latency_ms,
+                    "host_threads": F,
                     "api": "zk_msm_vartime(ctx, scalars_host, compressed_points_host, n, out32) from pinned host memory"},
             "gpu_launches": launches * world,
             "clocks": clocks,
             "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": macs / (acc_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12,
-                         "unit": "T(32x32+64 MAC)/s", "frac": macs / (acc_ms * 1e-3) / imad_peak, "traffic": None,
+                         "unit": "T(32x32+64 MAC)/s", "frac": macs / (acc_ms * 1e-3) / imad_peak,
+                         "traffic": NCU_ACCUM_DRAM_BYTES if (a.log2n == 20 and c == 16) else None,
                          "peak_source": "measured live: zk_bench_int_pipe(0), IMAD.WIDE.U32 carry chains on all SMs",
                          "kernel_ms": acc_ms, "phases_ms": {"decompress": phases[0], "digits_sort": phases[1], "bucket_accum": phases[2],
                                                             "reduce_encode": phases[3]},
                          "algorithmic": f"{adds:.0f} mixed adds x 7 fe_mul x {MAC_PER_FE_MUL} MAC"},
             "roofline_hbm": {"bound": "hbm", "kernel": "k_bucket_accum", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src},
+                             "unit": "GB/s", "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": NCU_ACCUM_DRAM_BYTES if (a.log2n == 20 and c == 16) else None, "algorithmic_bytes": alg_bytes, "peak_source": hbm_src},
             "blocked": BLOCKED,
         }
         if not a.no_cpu_baseline:

@@ -765,18 +765,15 @@ extern "C" int zk_ctx_last_phase_ms(zk_ctx* ctx, float out_ms[4]) {
 }
 extern "C" uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-// Window width by size: minimise W*(7n + 18*2^(c-1)) field multiplies subject to enough buckets to fill the chip.
+// Window width by size.  Measured on B200 (tools/sweep_windows.py, profiles/README.md): the widths whose TOP window is
+// either almost full (c = 15, 16: 13 of 253 bits left over) or carry-only (c = 11: 253 = 23*11) keep the bucket
+// occupancy even across windows; widths in between (12, 13, 14) concentrate the top window's points in a few
+// buckets and lose to them at every size.  Small MSMs are bound by the ~0.45 ms serial tail, so one width serves
+// them all.
 extern "C" int zk_pick_window(size_t n) {
-    int best = 4; double best_cost = 1e300;
-    for (int c = 4; c <= 16; c++) {
-        double W = 253 / c + 1, B = (double)(1u << (c - 1));
-        double cost = W * (7.0 * (double)n + 18.0 * B);
-        // a bucket thread is a serial chain of n/B adds: charge the chain when the grid cannot fill 148 SMs x 512 threads
-        double threads = W * B;
-        if (threads < 148.0 * 512.0) cost *= (148.0 * 512.0) / threads > 8.0 ? 8.0 : (148.0 * 512.0) / threads;
-        if (cost < best_cost) { best_cost = cost; best = c; }
-    }
-    return best;
+    if (n < ((size_t)1 << 14)) return 11;
+    if (n < ((size_t)1 << 20)) return 15;
+    return 16;
 }
 
 // ---- tables ----
