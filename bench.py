@@ -226,15 +226,16 @@ def run_cuda(a):
     np_scal = [t.numpy() for t in scal_host]; np_comp = [t.numpy() for t in comp_host]
 
     def step_e2e(i):
+        """One public-API call from host buffers on context i % F (blocking; returns the 32-byte encoding)."""
         f, s = i % F, i % SETS
-        r = zk.RistrettoPoint.optional_multiscalar_mul(ctxs[f], np_scal[s], np_comp[s])
-        if world > 1:
-            # sharded: this rank's partial came back as 32 bytes; one gather, rank 0 would add the G encodings
-            enc = torch.frombuffer(bytearray(bytes(r) + bytes(PARTIAL_BYTES - 32)), dtype=torch.uint8).to(dev)
-            with torch.cuda.stream(streams[f]):
-                dist.all_gather_into_tensor(gathered[f], enc.view(1, PARTIAL_BYTES))
-            streams[f].synchronize()
-        return r
+        return zk.RistrettoPoint.optional_multiscalar_mul(ctxs[f], np_scal[s], np_comp[s])
+
+    def gather_e2e(i, r):
+        """N > 1: this rank's partial came back as 32 bytes; one gather (issued from the main thread, in step order,
+        so every rank enqueues its collectives identically); rank 0 would add the G encodings."""
+        f = i % F
+        enc = torch.frombuffer(bytearray(bytes(r) + bytes(PARTIAL_BYTES - 32)), dtype=torch.uint8).to(dev)
+        dist.all_gather_into_tensor(gathered[f], enc.view(1, PARTIAL_BYTES))
 
     def barrier():
         if world > 1: dist.barrier()
@@ -292,9 +293,19 @@ def run_cuda(a):
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=F)
 
+    import queue
+
     def run_e2e(k):
-        futs = [pool.submit(lambda f=f: [step_e2e(i) for i in range(f, k, F)]) for f in range(F)]
-        return [x.result() for x in futs]
+        qs = [queue.Queue() for _ in range(F)]
+        futs = [pool.submit(lambda f=f: [qs[f].put(step_e2e(i)) for i in range(f, k, F)]) for f in range(F)]
+        out = []
+        for i in range(k):                      # results in step order
+            r = qs[i % F].get()
+            if world > 1: gather_e2e(i, r)
+            out.append(r)
+        for x in futs: x.result()
+        if world > 1: torch.cuda.synchronize()
+        return out
 
     run_e2e(W)
     barrier()
@@ -302,10 +313,12 @@ def run_cuda(a):
     res = run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
-    if world == 1 and bytes(res[0][0]) != bytes(r_dev):
+    if world == 1 and bytes(res[0]) != bytes(r_dev):
         raise SystemExit("parity gate failed inside the e2e loop")
     barrier(); t1 = time.perf_counter()
-    for i in range(3): step_e2e(i * F)
+    for i in range(3):
+        r = step_e2e(i * F)
+        if world > 1: gather_e2e(i * F, r); torch.cuda.synchronize()
     e2e_latency_ms = (time.perf_counter() - t1) / 3 * 1e3
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions
 
