@@ -66,7 +66,10 @@ __device__ __forceinline__ void st_ext(uint4* base, size_t idx, const ge_ext& r)
 // ---- point-format kernels --------------------------------------------------------------------
 
 // RFC 9496 4.3.1 over a batch; writes affine-Niels entries.  *bad = lowest rejected index.
-__global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
+#ifndef ZK_DEC_MINBLOCKS
+#define ZK_DEC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, ZK_DEC_MINBLOCKS) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
                                                     unsigned long long* __restrict__ bad, unsigned long long index_base) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -356,127 +359,41 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
 //     Wt = sum_i Wt_i + wc * sum_i i*A_i   (sum weighted by 1-based position inside the node)
 // At the leaves A_i = Wt_i = bucket i (wc = 1), and bucket i is itself the sum of its tasks' partials
 // (none for an empty bucket).  The root's Wt is the window sum  sum_b (b+1) * S_b.
-__device__ __forceinline__ void ge_shfl_xor(ge_ext& r, const ge_ext& p, int mask) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.X.v[i] = __shfl_xor_sync(0xffffffffu, p.X.v[i], mask);
-        r.Y.v[i] = __shfl_xor_sync(0xffffffffu, p.Y.v[i], mask);
-        r.Z.v[i] = __shfl_xor_sync(0xffffffffu, p.Z.v[i], mask);
-        r.T.v[i] = __shfl_xor_sync(0xffffffffu, p.T.v[i], mask);
-    }
-}
-constexpr uint32_t HEAVY_PARTIALS = 32;   // a bucket with more partials than this is summed by the whole warp
-
-// Leaf-level child = bucket `idx`: the sum of its tasks' partials (identity when it has none).  Must be called by
-// all 32 lanes (valid = false for lanes without a child): a bucket that was split into many tasks -- adversarial
-// scalars put up to n / TASK_LEN partials in ONE bucket -- is reduced by the warp together: strided partial
-// sums, then a shuffle butterfly.
-__device__ __forceinline__ void load_bucket(ge_ext& r, const uint4* __restrict__ partials, const uint32_t* __restrict__ task_off,
-                                            size_t idx, bool valid) {
-    uint32_t p0 = 0, p1 = 0;
-    if (valid) { p0 = task_off[idx]; p1 = task_off[idx + 1]; }
-    bool heavy = p1 - p0 > HEAVY_PARTIALS;
-    unsigned hmask = __ballot_sync(0xffffffffu, heavy);
-    ge_ext tmp;
-    if (!heavy) {
-        if (p0 == p1) ge_identity(r);
-        else {
-            ld_ext(r, partials, p0);
-#pragma unroll 1
-            for (uint32_t p = p0 + 1; p < p1; p++) { ld_ext(tmp, partials, p); ge_add(r, r, tmp); }
-        }
-    }
-    const int lane = threadIdx.x & 31;
-    while (hmask) {
-        int src = __ffs(hmask) - 1; hmask &= hmask - 1;
-        uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
-        ge_ext part; ge_identity(part);
-#pragma unroll 1
-        for (uint32_t p = q0 + lane; p < q1; p += 32) { ld_ext(tmp, partials, p); ge_add(part, part, tmp); }
-#pragma unroll 1
-        for (int o = 16; o >= 1; o >>= 1) { ge_shfl_xor(tmp, part, o); ge_add(part, part, tmp); }
-        if (lane == src) r = part;
-    }
-}
-#ifndef ZK_LEAF_MINBLOCKS
-#define ZK_LEAF_MINBLOCKS 2
-#endif
-__global__ void __launch_bounds__(128, ZK_LEAF_MINBLOCKS) k_tree_level(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in,
-                                                    const uint32_t* __restrict__ task_off, size_t m_in,
-                                                    size_t m_out, int windows, int log2_wc,
-                                                    uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t < m_out * (size_t)windows;      // inactive lanes still take part in the warp-wide leaf loads
-    size_t w = active ? t / m_out : 0, k = active ? t % m_out : 0;
-    size_t first = k * REDUCE_RADIX, last = first + REDUCE_RADIX;
-    if (last > m_in) last = m_in;
-    if (!active) last = first;
-    ge_ext run, acc, wsum, tmp;
-    ge_identity(run); ge_identity(acc); ge_identity(wsum);
-    // top-down running sum: after the loop run = sum A_i, acc = sum (i+1) A_i
-    if (task_off != nullptr) {
-        // leaf level: children are global bucket ids w*m_in + j, looked up through task_off
-#pragma unroll 1
-        for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
-            size_t j = first + jj;
-            bool valid = j < last;
-            load_bucket(tmp, a_in, task_off, w * m_in + j, valid);
-            if (valid) { ge_add(run, run, tmp); ge_add(acc, acc, run); }
-        }
-    } else {
-        const uint4* ain = a_in + w * m_in * 8;
-#pragma unroll 1
-        for (size_t j = last; j-- > first;) {
-            ld_ext(tmp, ain, j);
-            ge_add(run, run, tmp);
-            ge_add(acc, acc, run);
-        }
-    }
-    if (!active) return;
-    if (wt_in != nullptr) {
-        // acc - run = sum i*A_i ; scale by wc, add the children's weighted sums
-        ge_neg(tmp, run); ge_add(acc, acc, tmp);
-#pragma unroll 1
-        for (int d = 0; d < log2_wc; d++) ge_dbl(acc, acc);
-        const uint4* win = wt_in + w * m_in * 8;
-#pragma unroll 1
-        for (size_t j = first; j < last; j++) { ld_ext(tmp, win, j); ge_add(wsum, wsum, tmp); }
-        ge_add(acc, acc, wsum);
-    }
-    st_ext(a_out, t, run);
-    st_ext(wt_out, t, acc);
-}
-
 // ---- 4-lane cooperative point arithmetic ("quads") ----------------------------------------------
-// The upper tree levels and the window Horner are chains of dependent point operations with almost no
-// parallelism across threads, so their cost is the latency of one operation.  A quad = 4 adjacent lanes holding
-// one extended point, lane q owning one coordinate (0:X 1:Y 2:Z 3:T).  The 4 independent field multiplies of each
-// half of the HWCD formulas run in the 4 lanes at once (the layout dalek's AVX2 backend uses across vector lanes);
-// operands move between lanes with warp shuffles.  Depth per addition: 3 multiplies instead of 9; per doubling:
-// 1 squaring + 1 multiply instead of 4 + 4.  Every lane of the warp must execute these calls (full-mask shuffles):
-// roles are chosen with selects, never with branches.
-__device__ __forceinline__ void fe_shfl(fe& r, const fe& a, int src) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+// The reduction tree and the window Horner are chains of dependent point operations; register-hungry scalar
+// code runs them at 2 warps per scheduler.  A quad = 4 adjacent lanes holding one extended point, lane q owning
+// one coordinate (0:X 1:Y 2:Z 3:T).  The 4 independent field multiplies of each half of the HWCD formulas run in
+// the 4 lanes at once (the layout dalek's AVX2 backend uses across vector lanes); operands move between lanes
+// with warp shuffles restricted to the quad's own 4-lane mask, so quads of one warp may diverge from each other.
+// Depth per addition: 3 multiplies instead of 9; per doubling: 1 squaring + 1 multiply instead of 4 + 4; ~70
+// registers per thread.  Roles are chosen with selects, never with branches.
+struct quad_ctx { int q, base; unsigned mask; };
+__device__ __forceinline__ quad_ctx quad_self() {
+    quad_ctx c; c.q = threadIdx.x & 3; c.base = (threadIdx.x & 31) & ~3; c.mask = 0xfu << c.base; return c;
 }
-__device__ __forceinline__ void fe_shfl_xor(fe& r, const fe& a, int m) {
+__device__ __forceinline__ void fe_shfl(fe& r, const fe& a, int src, unsigned mask) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], m);
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(mask, a.v[i], src);
+}
+__device__ __forceinline__ void fe_shfl_xor(fe& r, const fe& a, int m, unsigned mask) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
 }
 __device__ __forceinline__ void quad_identity(fe& r, int q) { r = fe_zero(); r.v[0] = (q == 1 || q == 2) ? 1u : 0u; }
 // in: lane0 = E, lane1 = H, lane2 = F, lane3 = G.  out: (X3, Y3, Z3, T3) = (E*F, G*H, F*G, E*H) in lanes 0..3.
-__device__ __forceinline__ void quad_finish(fe& r, const fe& val, int q, int base) {
+__device__ __forceinline__ void quad_finish(fe& r, const fe& val, const quad_ctx& c) {
     fe m1, m2, x;
-    fe_shfl(m1, val, base + (q == 0 ? 2 : (q == 3 ? 0 : 3)));
-    fe_shfl(m2, val, base + 1);
-    fe_select(x, val, m2, q == 3);
+    fe_shfl(m1, val, c.base + (c.q == 0 ? 2 : (c.q == 3 ? 0 : 3)), c.mask);
+    fe_shfl(m2, val, c.base + 1, c.mask);
+    fe_select(x, val, m2, c.q == 3);
     fe_mul(r, x, m1);
 }
 // r = p + qq (both in quad layout).  Unified a = -1 addition, complete.
-__device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, int q, int base) {
+__device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const quad_ctx& c) {
+    const int q = c.q;
     const bool l0 = q == 0, hi = q >= 2;
     fe op, oq, a, b, dif, sum, u, v;
-    fe_shfl_xor(op, p, 1); fe_shfl_xor(oq, qq, 1);
+    fe_shfl_xor(op, p, 1, c.mask); fe_shfl_xor(oq, qq, 1, c.mask);
     fe_select(a, p, op, l0); fe_select(b, op, p, l0);          // lanes 0/1: a = Y1, b = X1
     fe_sub(dif, a, b); fe_add(sum, a, b);
     fe_select(u, sum, dif, l0); fe_select(u, u, p, hi);         // Y1-X1 | Y1+X1 | Z1 | T1
@@ -489,77 +406,133 @@ __device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, int q
     fe_mul(v, v, k);                                            // ... | ... | 2 Z2 | 2d T2
     fe r1, o;
     fe_mul(r1, u, v);                                           // A | B | D | C
-    fe_shfl_xor(o, r1, 1);
+    fe_shfl_xor(o, r1, 1, c.mask);
     fe_add(sum, r1, o);
     fe_select(a, r1, o, l0); fe_select(b, o, r1, l0);
     fe_sub(dif, a, b);                                          // lane0: B-A = E, lane2: D-C = F
     fe val; fe_select(val, dif, sum, (q & 1) != 0);             // lane1: B+A = H, lane3: D+C = G
-    quad_finish(r, val, q, base);
+    quad_finish(r, val, c);
 }
 // r = 2p.
-__device__ __forceinline__ void quad_dbl(fe& r, const fe& p, int q, int base) {
+__device__ __forceinline__ void quad_dbl(fe& r, const fe& p, const quad_ctx& c) {
+    const int q = c.q;
     fe x0, y0, s, opnd, sq, A, Bv, t, apb, bma, c2, L, R, val, z = fe_zero();
-    fe_shfl(x0, p, base); fe_shfl(y0, p, base + 1);
+    fe_shfl(x0, p, c.base, c.mask); fe_shfl(y0, p, c.base + 1, c.mask);
     fe_add(s, x0, y0);
     fe_select(opnd, p, s, q == 3);
     fe_sqr(sq, opnd);                                           // X^2 | Y^2 | Z^2 | (X+Y)^2
-    fe_shfl(A, sq, base); fe_shfl(Bv, sq, base + 1); fe_shfl(t, sq, base + 3);
+    fe_shfl(A, sq, c.base, c.mask); fe_shfl(Bv, sq, c.base + 1, c.mask); fe_shfl(t, sq, c.base + 3, c.mask);
     fe_add(apb, A, Bv); fe_sub(bma, Bv, A); fe_add(c2, sq, sq);
     fe_select(L, bma, t, q == 0); fe_select(L, L, z, q == 1);    // t | 0 | B-A | B-A
     fe_select(R, apb, c2, q == 2); fe_select(R, R, z, q == 3);   // A+B | A+B | 2Z^2 | 0
     fe_sub(val, L, R);                                          // E | H | F | G
-    quad_finish(r, val, q, base);
+    quad_finish(r, val, c);
 }
 __device__ __forceinline__ void quad_neg(fe& r, const fe& p, int q) { fe_cneg(r, p, q == 0 || q == 3); }
 __device__ __forceinline__ void quad_ld(fe& r, const uint4* base, size_t idx, int q) { ld_fe_plain(r, base + idx * 8 + q * 2); }
 __device__ __forceinline__ void quad_st(uint4* base, size_t idx, int q, const fe& r) { st_fe(base + idx * 8 + q * 2, r); }
 
-// Upper tree levels: one quad per node (see k_tree_level for the recurrence).  Trip counts are warp-uniform;
-// missing children are the identity.
-__global__ void __launch_bounds__(128) k_tree_level_quad(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in, size_t m_in,
+constexpr uint32_t HEAVY_PARTIALS = 24;   // a bucket with more partials than this is summed by the whole warp
+
+// Leaf-level child = bucket `idx`: the sum of its tasks' partials (identity when it has none).  Called by all 32
+// lanes at the same loop trip (valid = false for a quad without a child).  A bucket that was split into many tasks
+// -- adversarial scalars put up to n / TASK_LEN partials in ONE bucket -- is reduced by the 8 quads of the warp
+// together: strided partial sums, then a butterfly over quads.
+__device__ __forceinline__ void quad_load_bucket(fe& r, const uint4* __restrict__ partials, const uint32_t* __restrict__ task_off,
+                                                 size_t idx, bool valid, const quad_ctx& c) {
+    uint32_t p0 = 0, p1 = 0;
+    if (valid) { p0 = task_off[idx]; p1 = task_off[idx + 1]; }
+    const bool heavy = p1 - p0 > HEAVY_PARTIALS;
+    fe tmp;
+    if (!heavy) {
+        if (p0 == p1) quad_identity(r, c.q);
+        else {
+            quad_ld(r, partials, p0, c.q);
+#pragma unroll 1
+            for (uint32_t p = p0 + 1; p < p1; p++) { quad_ld(tmp, partials, p, c.q); quad_add(r, r, tmp, c); }
+        }
+    }
+    unsigned hmask = __ballot_sync(0xffffffffu, heavy);          // warp-wide rendezvous
+    const int lane = threadIdx.x & 31;
+    quad_ctx full = c; full.mask = 0xffffffffu;
+    while (hmask) {
+        int src = __ffs(hmask) - 1; hmask &= ~(0xfu << (src & ~3));
+        uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+        fe part; quad_identity(part, c.q);
+#pragma unroll 1
+        for (uint32_t p = q0 + (lane >> 2); p < q1; p += 8) { quad_ld(tmp, partials, p, c.q); quad_add(part, part, tmp, c); }
+#pragma unroll 1
+        for (int o = 16; o >= 4; o >>= 1) { fe_shfl_xor(tmp, part, o, 0xffffffffu); quad_add(part, part, tmp, full); }
+        if ((lane & ~3) == (src & ~3)) r = part;
+    }
+}
+
+// One quad per tree node.  A node covering children i = 0..7 (each of width `wc` buckets) combines
+//     A  = sum_i A_i                       (plain sum)
+//     Wt = sum_i Wt_i + wc * sum_i i*A_i   (sum weighted by 1-based position inside the node)
+// At the leaves (task_off != nullptr) A_i = Wt_i = bucket i, itself the sum of its tasks' partials.  The root's Wt
+// is the window sum  sum_b (b+1) * S_b.  Loop trip counts are warp-uniform; missing children are the identity.
+#ifndef ZK_TREE_MINBLOCKS
+#define ZK_TREE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in,
+                                                         const uint32_t* __restrict__ task_off, size_t m_in,
                                                          size_t m_out, int windows, int log2_wc,
                                                          uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
     size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int q = threadIdx.x & 3, base = (threadIdx.x & 31) & ~3;
+    const quad_ctx c = quad_self();
+    const int q = c.q;
     size_t t = gt >> 2;
     const bool active = t < m_out * (size_t)windows;
     size_t w = active ? t / m_out : 0, k = active ? t % m_out : 0;
     size_t first = k * REDUCE_RADIX;
-    const uint4* ain = a_in + w * m_in * 8;
-    const uint4* win = wt_in + w * m_in * 8;
     fe run, acc, wsum, tmp;
     quad_identity(run, q); quad_identity(acc, q); quad_identity(wsum, q);
+    if (task_off != nullptr) {
+        // leaf level: children are global bucket ids w*m_in + j, looked up through task_off
 #pragma unroll 1
-    for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
-        size_t j = first + jj;
-        bool valid = active && j < m_in;
-        if (valid) quad_ld(tmp, ain, j, q); else quad_identity(tmp, q);
-        quad_add(run, run, tmp, q, base);
-        quad_add(acc, acc, run, q, base);
-        if (valid) quad_ld(tmp, win, j, q); else quad_identity(tmp, q);
-        quad_add(wsum, wsum, tmp, q, base);
+        for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
+            size_t j = first + jj;
+            bool valid = active && j < m_in;
+            quad_load_bucket(tmp, a_in, task_off, w * m_in + j, valid, c);
+            quad_add(run, run, tmp, c);
+            quad_add(acc, acc, run, c);
+        }
+    } else {
+        const uint4* ain = a_in + w * m_in * 8;
+        const uint4* win = wt_in + w * m_in * 8;
+#pragma unroll 1
+        for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
+            size_t j = first + jj;
+            bool valid = active && j < m_in;
+            if (valid) quad_ld(tmp, ain, j, q); else quad_identity(tmp, q);
+            quad_add(run, run, tmp, c);
+            quad_add(acc, acc, run, c);
+            if (valid) quad_ld(tmp, win, j, q); else quad_identity(tmp, q);
+            quad_add(wsum, wsum, tmp, c);
+        }
+        quad_neg(tmp, run, q); quad_add(acc, acc, tmp, c);      // sum i*A_i
+#pragma unroll 1
+        for (int d = 0; d < log2_wc; d++) quad_dbl(acc, acc, c);
+        quad_add(acc, acc, wsum, c);
     }
-    quad_neg(tmp, run, q); quad_add(acc, acc, tmp, q, base);      // sum i*A_i
-#pragma unroll 1
-    for (int d = 0; d < log2_wc; d++) quad_dbl(acc, acc, q, base);
-    quad_add(acc, acc, wsum, q, base);
     if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
 }
 
-// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  One warp; every quad computes the same chain
-// (253 dependent doublings), quad 0 stores.
-__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int c, uint4* __restrict__ out_ext) {
-    const int q = threadIdx.x & 3, base = threadIdx.x & ~3;
+// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  One quad (253 dependent doublings).
+__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int cbits, uint4* __restrict__ out_ext) {
+    if (threadIdx.x >= 4) return;
+    const quad_ctx c = quad_self();
     fe acc, tmp;
-    quad_ld(acc, wt, windows - 1, q);
+    quad_ld(acc, wt, windows - 1, c.q);
 #pragma unroll 1
     for (int w = windows - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (int d = 0; d < c; d++) quad_dbl(acc, acc, q, base);
-        quad_ld(tmp, wt, w, q);
-        quad_add(acc, acc, tmp, q, base);
+        for (int d = 0; d < cbits; d++) quad_dbl(acc, acc, c);
+        quad_ld(tmp, wt, w, c.q);
+        quad_add(acc, acc, tmp, c);
     }
-    if (threadIdx.x < 4) quad_st(out_ext, 0, q, acc);
+    quad_st(out_ext, 0, c.q, acc);
 }
 
 __global__ void k_set_identity(uint4* __restrict__ out_ext) {
@@ -957,10 +930,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
-        if (w_in == nullptr)
-            k_tree_level<<<grid_for(m_out * W, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
-        else
-            k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, W, log2_wc, a_out, w_out);
+        k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
