@@ -98,6 +98,21 @@ int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32_host, cons
                          size_t n_static, const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host,
                          size_t n_dyn, uint8_t out32[32]);
 
+/* ---- batches of independent MSMs (one verdict per proof) ----
+ * m MSMs in ONE pass over the device: MSM k covers terms [seg_offsets[k], seg_offsets[k+1]) of the concatenated
+ * scalar/point arrays (seg_offsets has m+1 entries, seg_offsets[0] = 0).  out32s receives m encodings.  Small MSMs
+ * are latency-bound one at a time (253 dependent doublings in the window Horner); batched, they share every kernel
+ * launch and hide each other's serial tails.  This is the shape of "verify 1024 transactions, each with its own
+ * accept/reject": unlike folding all proofs into one MSM with random weights, one bad proof does not void the rest.
+ * An invalid encoding voids only its own MSM: valid[k] = 0 (if valid != NULL), out32s[k] = 0, and the call returns
+ * ZK_ERR_INVALID_POINT; all other results are still written. */
+int zk_msm_vartime_batch(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host,
+                         const uint64_t* seg_offsets, size_t m, uint8_t* out32s, uint8_t* valid);
+/* Same, every MSM running over the SAME cached points: MSM k = sum_j scalars[seg_offsets[k] + j] * table[offset + j]
+ * (m proofs verified against one set of static generators). */
+int zk_msm_vartime_table_batch(zk_ctx* ctx, const uint8_t* scalars32_host, const zk_table* t, size_t offset,
+                               const uint64_t* seg_offsets, size_t m, uint8_t* out32s);
+
 /* Device-resident form: scalars already in HBM (n*32 bytes), result left in HBM as an extended
  * point (X,Y,Z,T: 4 x 32-byte little-endian field elements, 128 bytes) so that per-GPU partial
  * sums can be gathered with one collective.  Asynchronous on the ctx stream. */

@@ -215,3 +215,56 @@ def test_sample_of_big_against_oracle(ctx, big, c_oracle):
     m = 1 << 15
     assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[5000:5000 + m], tab, offset=5000)) == \
         c_oracle.msm(sc[5000:5000 + m], comp[32 * 5000:32 * (5000 + m)], m, threads=8)
+
+
+# ---------------- batches of independent MSMs ----------------
+def test_batch_matches_individual_msms(ctx, c_oracle, rfc_vectors):
+    import zkvm_b200 as zk
+    sizes = [0, 1, 5, 300, 0, 1000, 189, 2048, 64, 7]
+    seg = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    n = int(seg[-1])
+    pts = make_points(c_oracle, n, 314); sc = rand_scalars(n, 314)
+    want = [c_oracle.msm(sc[int(a):int(b)], pts[32 * int(a):32 * int(b)], int(b - a), threads=2) for a, b in zip(seg, seg[1:])]
+    for c in (0, 5, 8, 13):
+        ctx.set_window(c)
+        got = zk.batch_optional_multiscalar_mul(ctx, sc, pts, seg)
+        assert [bytes(g) for g in got] == want, c
+    ctx.set_window(0)
+    assert want[0] == bytes(32) and want[4] == bytes(32)                    # empty MSM = identity
+    # one invalid encoding voids only its own MSM
+    bad = bytearray(pts); k = int(seg[5]) + 17
+    bad[32 * k:32 * k + 32] = H(rfc_vectors["bad_encodings"]["non_square"][1])
+    got = zk.batch_optional_multiscalar_mul(ctx, sc, bytes(bad), seg)
+    assert got[5] is None
+    assert [bytes(g) for i, g in enumerate(got) if i != 5] == [w for i, w in enumerate(want) if i != 5]
+
+
+def test_batch_many_small(ctx, c_oracle):
+    """1024 'transactions' of 256 terms each, every one with its own result."""
+    import zkvm_b200 as zk
+    m, per = 1024, 256
+    n = m * per
+    pts = make_points(c_oracle, n, 2718); sc = rand_scalars(n, 2718)
+    seg = np.arange(0, n + 1, per, dtype=np.uint64)
+    got = zk.batch_optional_multiscalar_mul(ctx, sc, pts, seg)
+    for k in (0, 1, 511, 1023):
+        assert bytes(got[k]) == c_oracle.msm(sc[k * per:(k + 1) * per], pts[32 * k * per:32 * (k + 1) * per], per)
+    # the batch adds up to the one big MSM over everything
+    assert c_oracle.point_sum(b"".join(bytes(g) for g in got), m) == bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts))
+
+
+def test_batch_over_shared_table(ctx, c_oracle):
+    """m proofs against one set of cached generators: MSM k uses table[offset : offset + len_k]."""
+    import zkvm_b200 as zk
+    gens = make_points(c_oracle, 3000, 1618)
+    tab = zk.PointTable(ctx).append_compressed(gens)
+    sizes = [2500, 0, 1, 777, 2500, 64]
+    seg = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    sc = rand_scalars(int(seg[-1]), 1618)
+    off = 123
+    got = zk.batch_vartime_multiscalar_mul(ctx, sc, tab, seg, offset=off)
+    for k, (a, b) in enumerate(zip(seg, seg[1:])):
+        a, b = int(a), int(b)
+        assert bytes(got[k]) == c_oracle.msm(sc[a:b], gens[32 * off:32 * (off + b - a)], b - a, threads=2), k
+    with pytest.raises(zk.ZkError):
+        zk.batch_vartime_multiscalar_mul(ctx, sc, tab, seg, offset=600)     # longest MSM would run past the table

@@ -35,6 +35,8 @@ SYMBOLS = [
     ("zk_msm_vartime", _i, [_vp, _vp, _vp, _sz, _vp]),
     ("zk_msm_vartime_table", _i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     ("zk_msm_vartime_mixed", _i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
+    ("zk_msm_vartime_batch", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    ("zk_msm_vartime_table_batch", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("zk_msm_table_dev", _i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     ("zk_ext_sum_compress_dev", _i, [_vp, _vp, _sz, _vp]),
     ("zk_encoding_is_identity", _i, [_vp]),

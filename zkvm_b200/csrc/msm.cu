@@ -63,6 +63,14 @@ __device__ __forceinline__ void st_ext(uint4* base, size_t idx, const ge_ext& r)
     st_fe(p, r.X); st_fe(p + 2, r.Y); st_fe(p + 4, r.Z); st_fe(p + 6, r.T);
 }
 
+// Batch mode: `seg` (M+1 ascending offsets, seg[0] = 0, seg[M] = n) splits the n terms into M independent MSMs.
+// MSM m owns windows [m*W, (m+1)*W) of the bucket space; everything downstream only sees "M*W windows".
+__device__ __forceinline__ uint32_t segment_of(const uint32_t* __restrict__ seg, uint32_t M, uint32_t i) {
+    uint32_t lo = 0, hi = M;                 // invariant: seg[lo] <= i < seg[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (seg[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
 // ---- point-format kernels --------------------------------------------------------------------
 
 // RFC 9496 4.3.1 over a batch; writes affine-Niels entries.  *bad = lowest rejected index.
@@ -70,7 +78,9 @@ __device__ __forceinline__ void st_ext(uint4* base, size_t idx, const ge_ext& r)
 #define ZK_DEC_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, ZK_DEC_MINBLOCKS) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
-                                                    unsigned long long* __restrict__ bad, unsigned long long index_base) {
+                                                    unsigned long long* __restrict__ bad, unsigned long long index_base,
+                                                    const uint32_t* __restrict__ seg = nullptr, uint32_t M = 0,
+                                                    uint32_t* __restrict__ bad_msm = nullptr) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
@@ -78,7 +88,12 @@ __global__ void __launch_bounds__(128, ZK_DEC_MINBLOCKS) k_decompress(const uint
     fe x, y, t;
     bool ok = ristretto_decode(x, y, t, w);
     ge_niels q;
-    if (ok) ge_to_niels_affine(q, x, y, t); else { ge_niels_identity(q); atomicMin(bad, index_base + (unsigned long long)i); }
+    if (ok) ge_to_niels_affine(q, x, y, t);
+    else {
+        ge_niels_identity(q);
+        atomicMin(bad, index_base + (unsigned long long)i);
+        if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;    // batch mode: only that MSM is void
+    }
     st_niels(table, i, q);
 }
 
@@ -156,20 +171,22 @@ __device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c, uint3
 }
 
 __global__ void __launch_bounds__(256) k_digit_hist(const uint4* __restrict__ scalars, size_t n, int c, int W,
-                                                    uint32_t* __restrict__ counts) {
+                                                    const uint32_t* __restrict__ seg, uint32_t M, uint32_t* __restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     scalar_reduce(s);
     uint32_t carry = 0; int B = 1 << (c - 1);
+    size_t wbase = seg ? (size_t)segment_of(seg, M, (uint32_t)i) * W : 0;
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
-        if (d != 0) atomicAdd(&counts[(size_t)w * B + (abs(d) - 1)], 1u);
+        if (d != 0) atomicAdd(&counts[(wbase + w) * B + (abs(d) - 1)], 1u);
     }
 }
 
 __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__ scalars, size_t n, int c, int W,
+                                                       const uint32_t* __restrict__ seg, uint32_t M, int shared_points,
                                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -177,11 +194,15 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     scalar_reduce(s);
     uint32_t carry = 0; int B = 1 << (c - 1);
+    uint32_t m = seg ? segment_of(seg, M, (uint32_t)i) : 0u;
+    size_t wbase = (size_t)m * W;
+    // the point of term i: the i-th point, or (every MSM of the batch runs over the SAME points) the (i - seg[m])-th
+    uint32_t pidx = shared_points ? (uint32_t)i - seg[m] : (uint32_t)i;
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
         if (d != 0) {
-            uint32_t pos = atomicAdd(&cursor[(size_t)w * B + (abs(d) - 1)], 1u);
-            entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+            uint32_t pos = atomicAdd(&cursor[(wbase + w) * B + (abs(d) - 1)], 1u);
+            entries[pos] = pidx | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -519,25 +540,43 @@ __global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(cons
     if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
 }
 
-// Horner over the per-window sums: out = sum_w 2^(c*w) * Wt_w.  One quad (253 dependent doublings).
-__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int cbits, uint4* __restrict__ out_ext) {
-    if (threadIdx.x >= 4) return;
+// Horner over the per-window sums: out[m] = sum_w 2^(c*w) * Wt[m*W + w].  One quad per MSM (253 dependent doublings).
+__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int cbits, uint32_t nmsm,
+                                                       uint4* __restrict__ out_ext) {
+    const uint32_t m = blockIdx.x * 8 + (threadIdx.x >> 2);
+    if (m >= nmsm) return;
     const quad_ctx c = quad_self();
+    const uint4* base = wt + (size_t)m * windows * 8;
     fe acc, tmp;
-    quad_ld(acc, wt, windows - 1, c.q);
+    quad_ld(acc, base, windows - 1, c.q);
 #pragma unroll 1
     for (int w = windows - 2; w >= 0; w--) {
 #pragma unroll 1
         for (int d = 0; d < cbits; d++) quad_dbl(acc, acc, c);
-        quad_ld(tmp, wt, w, c.q);
+        quad_ld(tmp, base, w, c.q);
         quad_add(acc, acc, tmp, c);
     }
-    quad_st(out_ext, 0, c.q, acc);
+    quad_st(out_ext, m, c.q, acc);
 }
 
 __global__ void k_set_identity(uint4* __restrict__ out_ext) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_ext p; ge_identity(p); st_ext(out_ext, 0, p);
+}
+
+// out32[m] = Encode(ext[m]), one thread per point
+__global__ void __launch_bounds__(64) k_encode_batch(const uint4* __restrict__ ext, size_t m, uint4* __restrict__ out32) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    ge_ext p; ld_ext(p, ext, i);
+    uint32_t o[8]; ristretto_encode(o, p);
+    out32[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out32[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+__global__ void k_set_identity_batch(uint4* __restrict__ out_ext, size_t m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    ge_ext p; ge_identity(p); st_ext(out_ext, i, p);
 }
 
 // out32 = Encode(sum of g extended points)
@@ -630,7 +669,7 @@ struct zk_ctx {
     bool join_aux = false;
     uint64_t launches = 0;
     // workspace
-    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, partials, task_off, tasks, plan, tree_a, tree_w, out_ext, out32, bad;
+    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, partials, task_off, tasks, plan, tree_a, tree_w, out_ext, out32, bad, seg, batch_ext, batch_out;
     uint8_t* h_out = nullptr;               // pinned 64 B: [0,32) encoding, [32,40) bad index
 };
 
@@ -709,7 +748,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->scalars, &ctx->comp, &ctx->dyn_table, &ctx->counts, &ctx->cursor, &ctx->offsets, &ctx->tiles,
-                      &ctx->entries, &ctx->partials, &ctx->task_off, &ctx->tasks, &ctx->plan, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad};
+                      &ctx->entries, &ctx->partials, &ctx->task_off, &ctx->tasks, &ctx->plan, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad, &ctx->seg, &ctx->batch_ext, &ctx->batch_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -747,6 +786,18 @@ extern "C" int zk_pick_window(size_t n) {
     if (n < ((size_t)1 << 14)) return 11;
     if (n < ((size_t)1 << 20)) return 15;
     return 16;
+}
+
+// Batches are throughput-bound (many MSMs hide each other's serial tails), so the width minimises the multiply
+// count W * (7 n + 36 * 2^(c-1)): n mixed adds per window plus two quad additions per bucket in the tree.
+static int pick_window_batch(size_t n_avg) {
+    int best = 4; double best_cost = 1e300;
+    for (int c = 4; c <= 16; c++) {
+        double W = 253 / c + 1, B = (double)(1u << (c - 1));
+        double cost = W * (7.0 * (double)(n_avg ? n_avg : 1) + 36.0 * B);
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
 }
 
 // ---- tables ----
@@ -860,23 +911,26 @@ extern "C" int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, 
 
 // ---- the MSM pipeline (asynchronous on ctx->stream) ----
 // scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
+// Batch mode (nmsm > 1): seg_dev = nmsm+1 offsets in HBM; out_ext_dev receives nmsm extended points.
 static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split, size_t n,
-                        void* out_ext_dev) {
+                        void* out_ext_dev, size_t nmsm = 1, const uint32_t* seg_dev = nullptr, bool shared_points = false) {
     cudaStream_t st = ctx->stream;
     if (n == 0) {
-        k_set_identity<<<1, 32, 0, st>>>((uint4*)out_ext_dev);
+        k_set_identity_batch<<<grid_for(nmsm, 128), 128, 0, st>>>((uint4*)out_ext_dev, nmsm);
         LAUNCH_CHECK(ctx);
         return ZK_OK;
     }
     if (n >= (1ull << 31)) return ZK_ERR_ARG;
-    const int c = ctx->forced_window ? ctx->forced_window : zk_pick_window(n);
-    const int W = 253 / c + 1;
+    const int c = ctx->forced_window ? ctx->forced_window : (nmsm > 1 ? pick_window_batch(n / nmsm) : zk_pick_window(n));
+    const int W1 = 253 / c + 1;                 // windows per MSM
+    const size_t W = (size_t)W1 * nmsm;         // windows in the whole batch
     const size_t B = (size_t)1 << (c - 1);
     const size_t NB = B * W;
+    if (NB >= (1ull << 31)) return ZK_ERR_ARG;
     const size_t ntiles = (NB + 1023) / 1024;
 
-    if ((unsigned long long)n * W >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
-    const size_t max_tasks = NB + (n * (size_t)W) / TASK_LEN;
+    if ((unsigned long long)n * W1 >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
+    const size_t max_tasks = NB + (n * (size_t)W1) / TASK_LEN;
     TRY(ensure(ctx, ctx->counts, NB * 4));
     TRY(ensure(ctx, ctx->cursor, NB * 4));
     TRY(ensure(ctx, ctx->offsets, (NB + 1) * 4));
@@ -884,7 +938,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
     TRY(ensure(ctx, ctx->tiles, ntiles * 8));
     TRY(ensure(ctx, ctx->plan, (TASK_LEN + 2) * 4));
     TRY(ensure(ctx, ctx->tasks, max_tasks * 8));
-    TRY(ensure(ctx, ctx->entries, n * W * 4));
+    TRY(ensure(ctx, ctx->entries, n * W1 * 4));
     TRY(ensure(ctx, ctx->partials, max_tasks * 128));
     size_t m1 = (B + REDUCE_RADIX - 1) / REDUCE_RADIX;
     TRY(ensure(ctx, ctx->tree_a, 2 * m1 * W * 128));     // ping-pong halves
@@ -893,7 +947,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
     CK(ctx, cudaMemsetAsync(ctx->plan.p, 0, (TASK_LEN + 2) * 4, st));
-    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->counts.p);
+    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, (uint32_t*)ctx->counts.p);
     LAUNCH_CHECK(ctx);
     k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (unsigned long long*)ctx->tiles.p,
                                                         (uint32_t*)ctx->plan.p);
@@ -904,8 +958,8 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
                                                     (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->task_off.p,
                                                     (uint32_t*)ctx->plan.p, (uint2*)ctx->tasks.p);
     LAUNCH_CHECK(ctx);
-    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W, (uint32_t*)ctx->cursor.p,
-                                                       (uint32_t*)ctx->entries.p);
+    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0,
+                                                       (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
 
@@ -930,12 +984,12 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
-        k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, W, log2_wc, a_out, w_out);
+        k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, (int)W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
     }
-    k_window_combine<<<1, 32, 0, st>>>(w_in, W, c, (uint4*)out_ext_dev);
+    k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, W1, c, (uint32_t)nmsm, (uint4*)out_ext_dev);
     LAUNCH_CHECK(ctx);
     return ZK_OK;
 }
@@ -985,6 +1039,31 @@ extern "C" int zk_msm_vartime_table(zk_ctx* ctx, const uint8_t* scalars32_host, 
     return finish_encode(ctx, ctx->out_ext.p, 1, out32);
 }
 
+// Upload n compressed points from the host and decode them into ctx->dyn_table, in chunks alternating between the
+// two side streams so that the copy of chunk i+1 overlaps the decode of chunk i.  The main stream is free to upload
+// scalars and sort digits meanwhile; msm_pipeline() joins the side streams right before the accumulation.
+// ctx->bad (lowest rejected index) must have been reset on the main stream.  Batch mode: seg/M/bad_msm mark the MSM.
+static int start_upload_decode(zk_ctx* ctx, const uint8_t* points32_host, size_t n, const uint32_t* seg_dev, uint32_t M,
+                               uint32_t* bad_msm_dev) {
+    if (n == 0) return ZK_OK;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaEventRecord(ctx->ev_fork, st));
+    const size_t chunk = n > (1u << 16) ? (n + 7) / 8 : n;
+    int which = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, which ^= 1) {
+        size_t cnt = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t sa = ctx->aux[which];
+        if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+        CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->comp.p + lo * 32, points32_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sa));
+        k_decompress<<<grid_for(cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
+                                                        (unsigned long long*)ctx->bad.p, (unsigned long long)lo, seg_dev, M, bad_msm_dev);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int i = 0; i < 2; i++) CK(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+    ctx->join_aux = true;
+    return ZK_OK;
+}
+
 extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32_host, const zk_table* t, size_t offset, size_t n_static,
                                     const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, uint8_t out32[32]) {
     if (!ctx || !out32) return ZK_ERR_ARG;
@@ -1000,24 +1079,7 @@ extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32
     cudaStream_t st = ctx->stream;
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], st));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
-    if (n_dyn) {
-        // upload + decode the points in chunks, alternating between the two side streams so that the copy of
-        // chunk i+1 overlaps the decode of chunk i; the scalars go up on the main stream behind them
-        CK(ctx, cudaEventRecord(ctx->ev_fork, st));
-        const size_t chunk = n_dyn > (1u << 16) ? (n_dyn + 7) / 8 : n_dyn;
-        int which = 0;
-        for (size_t lo = 0; lo < n_dyn; lo += chunk, which ^= 1) {
-            size_t cnt = n_dyn - lo < chunk ? n_dyn - lo : chunk;
-            cudaStream_t sa = ctx->aux[which];
-            if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
-            CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->comp.p + lo * 32, points_dyn32_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sa));
-            k_decompress<<<grid_for(cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
-                                                            (unsigned long long*)ctx->bad.p, (unsigned long long)lo);
-            LAUNCH_CHECK(ctx);
-        }
-        for (int i = 0; i < 2; i++) CK(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
-        ctx->join_aux = true;
-    }
+    TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
     if (n_static) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_static32_host, n_static * 32, cudaMemcpyHostToDevice, st));
     if (n_dyn) CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
@@ -1032,6 +1094,85 @@ extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32
 
 extern "C" int zk_msm_vartime(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, size_t n, uint8_t out32[32]) {
     return zk_msm_vartime_mixed(ctx, nullptr, nullptr, 0, 0, scalars32_host, points32_host, n, out32);
+}
+
+// ---- batches of independent MSMs -------------------------------------------------------------------
+static int batch_common(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, const zk_table* t, size_t offset,
+                        const uint64_t* seg_offsets, size_t m, uint8_t* out32s, uint8_t* valid) {
+    if (!ctx || !seg_offsets || !out32s || m == 0 || seg_offsets[0] != 0) return ZK_ERR_ARG;
+    const size_t n = (size_t)seg_offsets[m];
+    if (n >= (1ull << 31) || m >= (1ull << 24)) return ZK_ERR_ARG;
+    size_t longest = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (seg_offsets[i + 1] < seg_offsets[i]) return ZK_ERR_ARG;
+        size_t len = (size_t)(seg_offsets[i + 1] - seg_offsets[i]);
+        if (len > longest) longest = len;
+    }
+    if (n && !scalars32_host) return ZK_ERR_ARG;
+    if (t ? (offset > t->len || longest > t->len - offset) : (n && !points32_host)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    TRY(ensure(ctx, ctx->scalars, n * 32));
+    TRY(ensure(ctx, ctx->seg, (m + 1) * 4 + m * 4));          // offsets, then per-MSM reject flags
+    TRY(ensure(ctx, ctx->batch_ext, m * 128));
+    TRY(ensure(ctx, ctx->batch_out, m * 32));
+    TRY(ensure(ctx, ctx->bad, 8));
+    uint32_t* h_seg = (uint32_t*)malloc((m + 1) * 4);
+    if (!h_seg) return ZK_ERR_NOMEM;
+    for (size_t i = 0; i <= m; i++) h_seg[i] = (uint32_t)seg_offsets[i];
+    uint32_t* seg_dev = (uint32_t*)ctx->seg.p;
+    uint32_t* bad_msm_dev = seg_dev + (m + 1);
+    cudaError_t e = cudaMemcpyAsync(seg_dev, h_seg, (m + 1) * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // h_seg is pageable: finish the copy before freeing it
+    free(h_seg);
+    CK(ctx, e);
+    CK(ctx, cudaMemsetAsync(bad_msm_dev, 0, m * 4, st));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
+    const uint4* tab;
+    if (t) tab = t->d + offset * 6;
+    else {
+        TRY(ensure(ctx, ctx->comp, n * 32));
+        TRY(ensure(ctx, ctx->dyn_table, n * 96));
+        TRY(start_upload_decode(ctx, points32_host, n, seg_dev, (uint32_t)m, bad_msm_dev));
+        tab = (const uint4*)ctx->dyn_table.p;
+    }
+    if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, st));
+    TRY(msm_pipeline(ctx, ctx->scalars.p, tab, tab, (size_t)0xffffffffu, n, ctx->batch_ext.p, m, seg_dev, t != nullptr));
+    k_encode_batch<<<grid_for(m, 64), 64, 0, st>>>((const uint4*)ctx->batch_ext.p, m, (uint4*)ctx->batch_out.p);
+    LAUNCH_CHECK(ctx);
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], st));
+    CK(ctx, cudaMemcpyAsync(out32s, ctx->batch_out.p, m * 32, cudaMemcpyDeviceToHost, st));
+    uint32_t* h_bad = (uint32_t*)calloc(m, 4);
+    if (!h_bad) return ZK_ERR_NOMEM;
+    e = cudaMemcpyAsync(h_bad, bad_msm_dev, m * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    int rc = ZK_OK;
+    if (e == cudaSuccess && ctx->profiling) {
+        for (int i = 1; i < 4; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
+        }
+        ctx->phase_ms[0] = 0;
+    }
+    if (e == cudaSuccess) {
+        for (size_t i = 0; i < m; i++) {
+            if (h_bad[i]) { memset(out32s + 32 * i, 0, 32); rc = ZK_ERR_INVALID_POINT; }
+            if (valid) valid[i] = h_bad[i] ? 0 : 1;
+        }
+    }
+    free(h_bad);
+    CK(ctx, e);
+    return rc;
+}
+
+extern "C" int zk_msm_vartime_batch(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host,
+                                    const uint64_t* seg_offsets, size_t m, uint8_t* out32s, uint8_t* valid) {
+    return batch_common(ctx, scalars32_host, points32_host, nullptr, 0, seg_offsets, m, out32s, valid);
+}
+extern "C" int zk_msm_vartime_table_batch(zk_ctx* ctx, const uint8_t* scalars32_host, const zk_table* t, size_t offset,
+                                          const uint64_t* seg_offsets, size_t m, uint8_t* out32s) {
+    if (!t) return ZK_ERR_ARG;
+    return batch_common(ctx, scalars32_host, nullptr, t, offset, seg_offsets, m, out32s, nullptr);
 }
 
 extern "C" int zk_encoding_is_identity(const uint8_t enc32[32]) {

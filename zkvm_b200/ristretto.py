@@ -291,5 +291,43 @@ class RistrettoPoint:
         return CompressedRistretto(out.raw)
 
 
+def _seg_array(seg_offsets):
+    import numpy as np
+    seg = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+    if seg.ndim != 1 or len(seg) < 2 or seg[0] != 0:
+        raise ValueError("seg_offsets needs m+1 ascending entries starting at 0")
+    return seg
+
+
+def batch_optional_multiscalar_mul(ctx: Context, scalars, points, seg_offsets) -> list:
+    """m independent MSMs in one device pass: MSM k covers terms seg_offsets[k]:seg_offsets[k+1] of the concatenated
+    scalars / compressed points.  Returns a list of CompressedRistretto, with None where that MSM had an invalid
+    encoding (each proof keeps its own verdict)."""
+    hs, ns = _join32(scalars)
+    hp, np_ = _join32(points)
+    seg = _seg_array(seg_offsets)
+    m = len(seg) - 1
+    if ns != np_ or ns != int(seg[-1]):
+        raise ValueError("scalars/points/segments length mismatch")
+    out = C.create_string_buffer(32 * m)
+    valid = C.create_string_buffer(m)
+    rc = ctx._lib.zk_msm_vartime_batch(ctx._h, _ptr(hs), _ptr(hp), _ptr(seg), m, out, valid)
+    if rc not in (0, _lib.ZK_ERR_INVALID_POINT):
+        ctx._check(rc)
+    return [CompressedRistretto(out.raw[32 * k:32 * k + 32]) if valid.raw[k] else None for k in range(m)]
+
+
+def batch_vartime_multiscalar_mul(ctx: Context, scalars, table: "PointTable", seg_offsets, offset: int = 0) -> list:
+    """m MSMs over the SAME cached points: MSM k = sum_j scalars[seg[k] + j] * table[offset + j]."""
+    hs, ns = _join32(scalars)
+    seg = _seg_array(seg_offsets)
+    m = len(seg) - 1
+    if ns != int(seg[-1]):
+        raise ValueError("scalars/segments length mismatch")
+    out = C.create_string_buffer(32 * m)
+    ctx._check(ctx._lib.zk_msm_vartime_table_batch(ctx._h, _ptr(hs), table._h, offset, _ptr(seg), m, out))
+    return [CompressedRistretto(out.raw[32 * k:32 * k + 32]) for k in range(m)]
+
+
 def pick_window(n: int) -> int:
     return int(_lib.load().zk_pick_window(n))
