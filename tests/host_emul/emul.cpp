@@ -60,6 +60,10 @@ int emul_msm(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* o
         // so add r, then add q and subtract q again
         ge_add(acc, acc, r);
         ge_madd(acc, acc, q, false); ge_madd(acc, acc, q, true);
+        // ge_from_niels: +Q and -Q built from the table entry must cancel
+        ge_ext pq, nq; ge_from_niels(pq, q, false); ge_from_niels(nq, q, true);
+        ge_add(acc, acc, pq); ge_add(acc, acc, nq);
+        ge_add(acc, acc, pq); ge_madd(acc, acc, q, true);
     }
     uint32_t o[8]; ristretto_encode(o, acc); memcpy(out32, o, 32);
     return 0;

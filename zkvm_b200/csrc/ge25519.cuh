@@ -77,6 +77,19 @@ ZK_HD ZK_INLINE void ge_to_niels_affine(ge_niels& r, const fe& x, const fe& y, c
     fe_add(r.yp, y, x); fe_sub(r.ym, y, x); fe_mul(r.t2d, t, k);
 }
 
+// Extended form of +-Q from its Niels entry, at the cost of ONE multiply: (X:Y:Z:T) = (2x : 2y : 2 : 2xy), where
+// 2xy = t2d / d.  Used to start a bucket accumulator from its first point instead of adding it to the identity.
+ZK_HD ZK_INLINE void ge_from_niels(ge_ext& r, const ge_niels& q, bool neg) {
+    const fe dinv = {{0xcdc9f843u, 0x25e0f276u, 0x4279542eu, 0x0b5dd698u, 0xcdb9cf66u, 0x2b162114u, 0x14d5ce43u, 0x40907ed2u}};  // 1/d
+    fe x, t;
+    fe_sub(x, q.yp, q.ym);
+    fe_add(r.Y, q.yp, q.ym);
+    r.Z = fe_zero(); r.Z.v[0] = 2;
+    fe_mul(t, q.t2d, dinv);
+    fe_cneg(r.X, x, neg);
+    fe_cneg(r.T, t, neg);
+}
+
 // ---- ristretto255 ----
 
 // RFC 9496 4.3.1 Decode.  `w` = the 32 bytes as 8 little-endian words.  Returns false on any reject rule.

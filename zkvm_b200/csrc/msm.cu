@@ -198,12 +198,18 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     size_t wbase = (size_t)m * W;
     // the point of term i: the i-th point, or (every MSM of the batch runs over the SAME points) the (i - seg[m])-th
     uint32_t pidx = shared_points ? (uint32_t)i - seg[m] : (uint32_t)i;
-    for (int w = 0; w < W; w++) {
-        int d = next_digit(s, w, c, carry);
-        if (d != 0) {
-            uint32_t pos = atomicAdd(&cursor[(wbase + w) * B + (abs(d) - 1)], 1u);
-            entries[pos] = pidx | (d < 0 ? 0x80000000u : 0u);
+    // 8 windows at a time: the 8 returning atomics are issued back to back, then the 8 stores
+    for (int w0 = 0; w0 < W; w0 += 8) {
+        uint32_t pos[8], val[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int w = w0 + k;
+            int d = w < W ? next_digit(s, w, c, carry) : 0;
+            val[k] = d != 0 ? (pidx | (d < 0 ? 0x80000000u : 0u)) : 0xffffffffu;
+            pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + w) * B + (abs(d) - 1)], 1u) : 0u;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
     }
 }
 
@@ -349,8 +355,9 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
     uint2 d = tasks[t];
     uint32_t lo = offsets[d.x] + d.y * TASK_LEN, end = offsets[d.x + 1];
     uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
-    ge_ext acc; ge_identity(acc);
+    ge_ext acc;
 #if ZK_ACCUM_PREFETCH
+    ge_identity(acc);
     // software pipeline: the index two entries ahead and the point one entry ahead are in flight during a madd
     uint32_t e0 = entries[lo];                       // a task is never empty
     uint32_t e1 = lo + 1 < hi ? entries[lo + 1] : 0u;
@@ -364,8 +371,13 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
         q = qn; e0 = e1; e1 = e2;
     }
 #else
+    {   // a task is never empty: start from its first point (1 multiply) instead of identity + point (7)
+        uint32_t e = entries[lo];
+        ge_niels q; ld_point(q, tab_a, tab_b, split, e);
+        ge_from_niels(acc, q, (e >> 31) != 0);
+    }
 #pragma unroll 1
-    for (uint32_t k = lo; k < hi; k++) {
+    for (uint32_t k = lo + 1; k < hi; k++) {
         uint32_t e = entries[k];
         ge_niels q; ld_point(q, tab_a, tab_b, split, e);
         ge_madd(acc, acc, q, (e >> 31) != 0);
