@@ -160,9 +160,23 @@ ZK_HD ZK_INLINE void fe_sqr_n(fe& r, const fe& a, int n) {
     for (int i = 1; i < n; i++) fe_sqr(r, r);
 }
 
-// r = a^(2^252 - 3) = a^((p-5)/8).  Standard 2^k-1 ladder: 251 squarings + 11 multiplies.
-ZK_HD inline void fe_pow22523(fe& r, const fe& z) {
-    fe t0, t1, t2;
+// Two field elements advanced in lockstep: the exponentiation chains below are 250 dependent squarings, so running
+// two of them interleaved doubles the instruction-level parallelism a thread offers the IMAD pipe.
+struct fe2 { fe a, b; };
+ZK_HD ZK_INLINE void fe_mul(fe2& r, const fe2& x, const fe2& y) { fe_mul(r.a, x.a, y.a); fe_mul(r.b, x.b, y.b); }
+ZK_HD ZK_INLINE void fe_sqr(fe2& r, const fe2& x) { fe_sqr(r.a, x.a); fe_sqr(r.b, x.b); }
+ZK_HD ZK_INLINE void fe_sqr_n(fe2& r, const fe2& x, int n) {
+    fe_sqr(r, x);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 1; i < n; i++) fe_sqr(r, r);
+}
+
+// r = a^(2^252 - 3) = a^((p-5)/8).  Standard 2^k-1 ladder: 251 squarings + 11 multiplies.  F = fe or fe2.
+template <class F>
+ZK_HD inline void fe_pow22523_t(F& r, const F& z) {
+    F t0, t1, t2;
     fe_sqr(t0, z);                 // 2
     fe_sqr_n(t1, t0, 2);           // 8
     fe_mul(t1, z, t1);             // 9
@@ -186,6 +200,7 @@ ZK_HD inline void fe_pow22523(fe& r, const fe& z) {
     fe_sqr_n(t0, t0, 2);           // 2^252-4
     fe_mul(r, t0, z);              // 2^252-3
 }
+ZK_HD inline void fe_pow22523(fe& r, const fe& z) { fe_pow22523_t<fe>(r, z); }
 
 // r = a^(p-2) = a^(2^255-21).
 ZK_HD inline void fe_invert(fe& r, const fe& z) {
@@ -198,14 +213,18 @@ ZK_HD inline void fe_invert(fe& r, const fe& z) {
 }
 
 // RFC 9496 section 4.2 SQRT_RATIO_M1(u, v): returns was_square, r = |sqrt(u/v)| or |sqrt(i*u/v)|.
-ZK_HD inline bool fe_sqrt_ratio_m1(fe& r, const fe& u, const fe& v) {
-    fe v3, v7, t, check, nu, nui;
-    fe_sqr(v3, v); fe_mul(v3, v3, v);          // v^3
-    fe_sqr(v7, v3); fe_mul(v7, v7, v);         // v^7
-    fe_mul(t, u, v7);
-    fe_pow22523(t, t);
-    fe_mul(t, t, v3); fe_mul(t, t, u);         // r = u v^3 (u v^7)^((p-5)/8)
-    fe_sqr(check, t); fe_mul(check, check, v); // v r^2
+// Split around the exponentiation so that two instances can share one interleaved chain.
+struct sqrt_ratio_state { fe v3, t; };
+ZK_HD ZK_INLINE void fe_sqrt_ratio_pre(sqrt_ratio_state& st, const fe& u, const fe& v) {
+    fe v7;
+    fe_sqr(st.v3, v); fe_mul(st.v3, st.v3, v);          // v^3
+    fe_sqr(v7, st.v3); fe_mul(v7, v7, v);               // v^7
+    fe_mul(st.t, u, v7);                                // the value to raise to (p-5)/8
+}
+ZK_HD ZK_INLINE bool fe_sqrt_ratio_post(fe& r, const sqrt_ratio_state& st, const fe& powed, const fe& u, const fe& v) {
+    fe t, check, nu, nui;
+    fe_mul(t, powed, st.v3); fe_mul(t, t, u);           // r = u v^3 (u v^7)^((p-5)/8)
+    fe_sqr(check, t); fe_mul(check, check, v);          // v r^2
     fe_neg(nu, u);
     fe i = fe_sqrt_m1();
     fe_mul(nui, nu, i);
@@ -216,6 +235,12 @@ ZK_HD inline bool fe_sqrt_ratio_m1(fe& r, const fe& u, const fe& v) {
     fe_select(t, t, ri, flipped | flipped_i);
     fe_abs(r, t);
     return correct | flipped;
+}
+ZK_HD inline bool fe_sqrt_ratio_m1(fe& r, const fe& u, const fe& v) {
+    sqrt_ratio_state st; fe p;
+    fe_sqrt_ratio_pre(st, u, v);
+    fe_pow22523(p, st.t);
+    return fe_sqrt_ratio_post(r, st, p, u, v);
 }
 
 }  // namespace zk

@@ -92,30 +92,52 @@ ZK_HD ZK_INLINE void ge_from_niels(ge_ext& r, const ge_niels& q, bool neg) {
 
 // ---- ristretto255 ----
 
-// RFC 9496 4.3.1 Decode.  `w` = the 32 bytes as 8 little-endian words.  Returns false on any reject rule.
-// On success writes the affine representative (x, y, t = xy), Z = 1.
-ZK_HD inline bool ristretto_decode(fe& x, fe& y, fe& t, const uint32_t w[8]) {
-    fe s;
-    bool canonical = fe_from_words(s, w);
+// RFC 9496 4.3.1 Decode, split around the inverse square root.  `w` = the 32 bytes as 8 little-endian words.
+struct decode_state { fe s, u1, u2, v, arg; bool early_ok; };
+ZK_HD ZK_INLINE void ristretto_decode_pre(decode_state& d, const uint32_t w[8]) {
+    bool canonical = fe_from_words(d.s, w);
     bool s_neg = (w[0] & 1u) != 0;
-    fe ss, u1, u2, u2s, v, one = fe_one(), isr, dx, dy, tmp;
-    fe_sqr(ss, s);
-    fe_sub(u1, one, ss);
-    fe_add(u2, one, ss);
-    fe_sqr(u2s, u2);
-    fe dd = fe_d();
-    fe_sqr(tmp, u1); fe_mul(tmp, tmp, dd); fe_neg(tmp, tmp);
-    fe_sub(v, tmp, u2s);                          // v = -(d u1^2) - u2^2
-    fe_mul(tmp, v, u2s);
-    bool was_square = fe_sqrt_ratio_m1(isr, one, tmp);
-    fe_mul(dx, isr, u2);
-    fe_mul(dy, isr, dx); fe_mul(dy, dy, v);
-    fe_mul(tmp, s, dx); fe_dbl(tmp, tmp);
+    d.early_ok = canonical & !s_neg;
+    fe ss, u2s, tmp, one = fe_one(), dd = fe_d();
+    fe_sqr(ss, d.s);
+    fe_sub(d.u1, one, ss);
+    fe_add(d.u2, one, ss);
+    fe_sqr(u2s, d.u2);
+    fe_sqr(tmp, d.u1); fe_mul(tmp, tmp, dd); fe_neg(tmp, tmp);
+    fe_sub(d.v, tmp, u2s);                        // v = -(d u1^2) - u2^2
+    fe_mul(d.arg, d.v, u2s);                      // SQRT_RATIO_M1(1, v * u2^2)
+}
+// On success writes the affine representative (x, y, t = xy), Z = 1.
+ZK_HD ZK_INLINE bool ristretto_decode_post(fe& x, fe& y, fe& t, const decode_state& d, const fe& isr, bool was_square) {
+    fe dx, dy, tmp;
+    fe_mul(dx, isr, d.u2);
+    fe_mul(dy, isr, dx); fe_mul(dy, dy, d.v);
+    fe_mul(tmp, d.s, dx); fe_dbl(tmp, tmp);
     fe_abs(x, tmp);
-    fe_mul(y, u1, dy);
+    fe_mul(y, d.u1, dy);
     fe_mul(t, x, y);
-    bool bad = !canonical | s_neg | !was_square | fe_is_negative(t) | fe_is_zero(y);
+    bool bad = !d.early_ok | !was_square | fe_is_negative(t) | fe_is_zero(y);
     return !bad;
+}
+// Returns false on any reject rule.
+ZK_HD inline bool ristretto_decode(fe& x, fe& y, fe& t, const uint32_t w[8]) {
+    decode_state d; fe isr, one = fe_one();
+    ristretto_decode_pre(d, w);
+    bool was_square = fe_sqrt_ratio_m1(isr, one, d.arg);
+    return ristretto_decode_post(x, y, t, d, isr, was_square);
+}
+// Two decodes sharing one interleaved exponentiation chain (see fe2).
+ZK_HD inline void ristretto_decode_x2(fe& x0, fe& y0, fe& t0, bool& ok0, const uint32_t w0[8],
+                                      fe& x1, fe& y1, fe& t1, bool& ok1, const uint32_t w1[8]) {
+    decode_state d0, d1; sqrt_ratio_state s0, s1; fe one = fe_one(), isr0, isr1;
+    ristretto_decode_pre(d0, w0); ristretto_decode_pre(d1, w1);
+    fe_sqrt_ratio_pre(s0, one, d0.arg); fe_sqrt_ratio_pre(s1, one, d1.arg);
+    fe2 z, p; z.a = s0.t; z.b = s1.t;
+    fe_pow22523_t<fe2>(p, z);
+    bool sq0 = fe_sqrt_ratio_post(isr0, s0, p.a, one, d0.arg);
+    bool sq1 = fe_sqrt_ratio_post(isr1, s1, p.b, one, d1.arg);
+    ok0 = ristretto_decode_post(x0, y0, t0, d0, isr0, sq0);
+    ok1 = ristretto_decode_post(x1, y1, t1, d1, isr1, sq1);
 }
 
 // RFC 9496 4.3.2 Encode.  Output: canonical 8 little-endian words.

@@ -74,13 +74,37 @@ __device__ __forceinline__ uint32_t segment_of(const uint32_t* __restrict__ seg,
 // ---- point-format kernels --------------------------------------------------------------------
 
 // RFC 9496 4.3.1 over a batch; writes affine-Niels entries.  *bad = lowest rejected index.
-#ifndef ZK_DEC_MINBLOCKS
-#define ZK_DEC_MINBLOCKS 4
+#ifndef ZK_DEC_PAIR
+#define ZK_DEC_PAIR 0   // measured: 2.16 ms vs 1.98 ms at 2^20 (205 registers halve the occupancy); kept for the record
 #endif
-__global__ void __launch_bounds__(128, ZK_DEC_MINBLOCKS) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
+// Each thread decodes points 2t and 2t+1 with one interleaved exponentiation chain (ZK_DEC_PAIR), see fe2.
+__global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
                                                     unsigned long long* __restrict__ bad, unsigned long long index_base,
                                                     const uint32_t* __restrict__ seg = nullptr, uint32_t M = 0,
                                                     uint32_t* __restrict__ bad_msm = nullptr) {
+#if ZK_DEC_PAIR
+    size_t i0 = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    size_t i1 = i0 + 1 < n ? i0 + 1 : i0;            // odd tail: decode the last point twice, store it once
+    uint4 a0 = __ldg(in + 2 * i0), b0 = __ldg(in + 2 * i0 + 1), a1 = __ldg(in + 2 * i1), b1 = __ldg(in + 2 * i1 + 1);
+    uint32_t w0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+    uint32_t w1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
+    fe x[2], y[2], t[2]; bool ok[2];
+    ristretto_decode_x2(x[0], y[0], t[0], ok[0], w0, x[1], y[1], t[1], ok[1], w1);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        size_t i = k ? i1 : i0;
+        if (k && i1 == i0) break;
+        ge_niels q;
+        if (ok[k]) ge_to_niels_affine(q, x[k], y[k], t[k]);
+        else {
+            ge_niels_identity(q);
+            atomicMin(bad, index_base + (unsigned long long)i);
+            if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;    // batch mode: only that MSM is void
+        }
+        st_niels(table, i, q);
+    }
+#else
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
@@ -92,9 +116,10 @@ __global__ void __launch_bounds__(128, ZK_DEC_MINBLOCKS) k_decompress(const uint
     else {
         ge_niels_identity(q);
         atomicMin(bad, index_base + (unsigned long long)i);
-        if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;    // batch mode: only that MSM is void
+        if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;
     }
     st_niels(table, i, q);
+#endif
 }
 
 // RFC 9496 4.3.4 over a batch of 64-byte strings; normalises to Z = 1 and writes affine-Niels entries.
@@ -338,6 +363,9 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
 #ifndef ZK_ACCUM_MINBLOCKS
 #define ZK_ACCUM_MINBLOCKS 3
 #endif
+#ifndef ZK_ACCUM_L2PREFETCH
+#define ZK_ACCUM_L2PREFETCH 1
+#endif
 #ifndef ZK_ACCUM_PREFETCH
 #define ZK_ACCUM_PREFETCH 0
 #endif
@@ -376,12 +404,30 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
         ge_niels q; ld_point(q, tab_a, tab_b, split, e);
         ge_from_niels(acc, q, (e >> 31) != 0);
     }
+#if ZK_ACCUM_L2PREFETCH
+    uint32_t e = lo + 1 < hi ? entries[lo + 1] : 0u;
+#pragma unroll 1
+    for (uint32_t k = lo + 1; k < hi; k++) {
+        // next index one iteration ahead; its point is pulled towards the SM with prefetches (no registers held)
+        uint32_t en = k + 1 < hi ? entries[k + 1] : e;
+        {
+            uint32_t idx = en & 0x7fffffffu;
+            const uint4* pp = idx < split ? tab_a + (size_t)idx * 6 : tab_b + (size_t)(idx - split) * 6;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 4));
+        }
+        ge_niels q; ld_point(q, tab_a, tab_b, split, e);
+        ge_madd(acc, acc, q, (e >> 31) != 0);
+        e = en;
+    }
+#else
 #pragma unroll 1
     for (uint32_t k = lo + 1; k < hi; k++) {
         uint32_t e = entries[k];
         ge_niels q; ld_point(q, tab_a, tab_b, split, e);
         ge_madd(acc, acc, q, (e >> 31) != 0);
     }
+#endif
 #endif
     st_ext(partials, task_off[d.x] + d.y, acc);
 }
@@ -857,7 +903,7 @@ static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* ta
     if (n == 0) return ZK_OK;
     TRY(ensure(ctx, ctx->bad, 8));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
-    k_decompress<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
+    k_decompress<<<grid_for(ZK_DEC_PAIR ? (n + 1) / 2 : n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
                                                              (unsigned long long*)ctx->bad.p, 0ull);
     LAUNCH_CHECK(ctx);
     if (!sync) return ZK_OK;
@@ -1067,7 +1113,7 @@ static int start_upload_decode(zk_ctx* ctx, const uint8_t* points32_host, size_t
         cudaStream_t sa = ctx->aux[which];
         if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
         CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->comp.p + lo * 32, points32_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sa));
-        k_decompress<<<grid_for(cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
+        k_decompress<<<grid_for(ZK_DEC_PAIR ? (cnt + 1) / 2 : cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
                                                         (unsigned long long*)ctx->bad.p, (unsigned long long)lo, seg_dev, M, bad_msm_dev);
         LAUNCH_CHECK(ctx);
     }
