@@ -75,6 +75,14 @@ int zk_table_append_compressed_dev(zk_ctx* ctx, zk_table* t, const void* points3
 /* Hash-to-group (RFC 9496 4.3.4) of n 64-byte strings, appended. */
 int zk_table_append_uniform(zk_ctx* ctx, zk_table* t, const uint8_t* bytes64_host, size_t n);
 int zk_table_append_uniform_dev(zk_ctx* ctx, zk_table* t, const void* bytes64_dev, size_t n);
+/* Append n already-decompressed points given in extended coordinates: X, Y, Z, T as 4 x 32-byte canonical
+ * little-endian field elements (128 bytes per point; any projective representative with Z != 0).  Stands behind
+ * "the caller holds Vec<RistrettoPoint>" (dalek's RistrettoPoint is four field elements; FieldElement::to_bytes
+ * gives this form without the inversion + square root a CPU-side compress() would cost).  Normalised to Z = 1 on the
+ * device.  ZK_ERR_INVALID_POINT (+ lowest index) for a non-canonical coordinate, Z = 0, an off-curve point or
+ * T*Z != X*Y; nothing is appended then. */
+int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index);
+int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index);
 /* Encode table[offset .. offset+n) (RFC 9496 4.3.2) into out32 (n*32 bytes). */
 int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, uint8_t* out32_host);
 int zk_table_compress_dev(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, void* out32_dev);

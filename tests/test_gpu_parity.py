@@ -268,3 +268,36 @@ def test_batch_over_shared_table(ctx, c_oracle):
         assert bytes(got[k]) == c_oracle.msm(sc[a:b], gens[32 * off:32 * (off + b - a)], b - a, threads=2), k
     with pytest.raises(zk.ZkError):
         zk.batch_vartime_multiscalar_mul(ctx, sc, tab, seg, offset=600)     # longest MSM would run past the table
+
+
+def test_extended_point_ingestion(ctx, rfc_vectors):
+    """Decompressed points handed over as (X, Y, Z, T): any projective representative, any coset member."""
+    import random
+    import zkvm_b200 as zk
+    from oracle import ristretto255_ref as ref
+    rnd = random.Random(9)
+    P = ref.P
+    blob, want = b"", b""
+    for h in rfc_vectors["generator_multiples"]:
+        pt = ref.decode(H(h))
+        lam = rnd.getrandbits(250) + 2
+        # a different member of the same ristretto coset (add 4-torsion), scaled projectively
+        q = ref.Point(pt.Y * ref.SQRT_M1, pt.X * ref.SQRT_M1, pt.Z, -pt.T) if rnd.random() < 0.5 else pt
+        blob += b"".join((v * lam % P).to_bytes(32, "little") for v in (q.X, q.Y, q.Z, q.T))
+        want += H(h)
+    t = zk.PointTable(ctx).append_extended(blob)
+    assert t.compress() == want
+    sc = rand_scalars(16, 4)
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, t)) == ref.msm_naive([bytes(r) for r in sc], [want[32 * i:32 * i + 32] for i in range(16)])
+    good = blob[128:256]
+    B = ref.BASEPOINT
+    for name, bad in {
+        "off curve": b"".join(v.to_bytes(32, "little") for v in (B.X, (B.Y + 1) % P, 1, B.X * (B.Y + 1) % P)),
+        "T inconsistent": b"".join(v.to_bytes(32, "little") for v in (B.X, B.Y, 1, (B.T + 1) % P)),
+        "Z zero": b"".join(v.to_bytes(32, "little") for v in (B.X, B.Y, 0, B.T)),
+        "non-canonical coordinate": b"".join(v.to_bytes(32, "little") for v in (B.X + P, B.Y, 1, B.T)),
+    }.items():
+        tt = zk.PointTable(ctx)
+        with pytest.raises(zk.InvalidPoint) as e:
+            tt.append_extended(good * 3 + bad + good)
+        assert e.value.index == 3 and len(tt) == 0, name

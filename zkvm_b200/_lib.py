@@ -30,6 +30,8 @@ SYMBOLS = [
     ("zk_table_append_compressed_dev", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     ("zk_table_append_uniform", _i, [_vp, _vp, _vp, _sz]),
     ("zk_table_append_uniform_dev", _i, [_vp, _vp, _vp, _sz]),
+    ("zk_table_append_extended", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    ("zk_table_append_extended_dev", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     ("zk_table_compress", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("zk_table_compress_dev", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("zk_msm_vartime", _i, [_vp, _vp, _vp, _sz, _vp]),

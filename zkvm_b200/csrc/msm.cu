@@ -142,6 +142,35 @@ __global__ void __launch_bounds__(128) k_from_uniform(const uint4* __restrict__ 
     st_niels(table, i, q);
 }
 
+// Extended points (X, Y, Z, T as 4 x 32-byte little-endian field elements; any representative, any Z != 0) ->
+// affine-Niels entries.  This is how a caller that already holds decompressed points (dalek `RistrettoPoint` =
+// four field elements) hands them over without compressing them on the CPU.  Rejected (index reported): a
+// non-canonical field encoding, Z = 0, a point off the curve -x^2 + y^2 = 1 + d x^2 y^2, or T*Z != X*Y.
+__global__ void __launch_bounds__(128) k_from_extended(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
+                                                       unsigned long long* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe c[4]; bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 a = __ldg(in + 8 * i + 2 * k), b = __ldg(in + 8 * i + 2 * k + 1);
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        ok &= fe_from_words(c[k], w);
+    }
+    fe zi, x, y, t, xx, yy, lhs, rhs, tmp, one = fe_one(), dd = fe_d();
+    ok &= !fe_is_zero(c[2]);
+    fe_invert(zi, c[2]);
+    fe_mul(x, c[0], zi); fe_mul(y, c[1], zi); fe_mul(t, x, y);
+    fe_mul(tmp, c[3], zi); ok &= fe_eq(tmp, t);                        // T/Z == (X/Z)(Y/Z)
+    fe_sqr(xx, x); fe_sqr(yy, y);
+    fe_sub(lhs, yy, xx);
+    fe_mul(rhs, xx, yy); fe_mul(rhs, rhs, dd); fe_add(rhs, rhs, one);
+    ok &= fe_eq(lhs, rhs);
+    ge_niels q;
+    if (ok) ge_to_niels_affine(q, x, y, t); else { ge_niels_identity(q); atomicMin(bad, (unsigned long long)i); }
+    st_niels(table, i, q);
+}
+
 __device__ __forceinline__ void niels_to_ext(ge_ext& p, const ge_niels& q) {
     // (2x : 2y : 2 : 2xy);  T = X*Y/Z = X*Y*2^-1
     fe inv2 = {{0xfffffff7u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu}};
@@ -617,11 +646,6 @@ __global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__
     quad_st(out_ext, m, c.q, acc);
 }
 
-__global__ void k_set_identity(uint4* __restrict__ out_ext) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    ge_ext p; ge_identity(p); st_ext(out_ext, 0, p);
-}
-
 // out32[m] = Encode(ext[m]), one thread per point
 __global__ void __launch_bounds__(64) k_encode_batch(const uint4* __restrict__ ext, size_t m, uint4* __restrict__ out32) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -947,6 +971,30 @@ extern "C" int zk_table_append_uniform(zk_ctx* ctx, zk_table* t, const uint8_t* 
     TRY(ensure(ctx, ctx->comp, n * 64));
     CK(ctx, cudaMemcpyAsync(ctx->comp.p, bytes64_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     return zk_table_append_uniform_dev(ctx, t, ctx->comp.p, n);
+}
+extern "C" int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index) {
+    if (!ctx || !t || (!ext128_dev && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(table_reserve(ctx, t, t->len + n));
+    if (n == 0) return ZK_OK;
+    TRY(ensure(ctx, ctx->bad, 8));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
+    k_from_extended<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)ext128_dev, n, t->d + t->len * 6,
+                                                                (unsigned long long*)ctx->bad.p);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
+    if (b != ~0ull) { if (bad_index) *bad_index = (size_t)b; return ZK_ERR_INVALID_POINT; }
+    t->len += n;
+    return ZK_OK;
+}
+extern "C" int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index) {
+    if (!ctx || !t || (!ext128_host && n)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->comp, n * 128));
+    CK(ctx, cudaMemcpyAsync(ctx->comp.p, ext128_host, n * 128, cudaMemcpyHostToDevice, ctx->stream));
+    return zk_table_append_extended_dev(ctx, t, ctx->comp.p, n, bad_index);
 }
 extern "C" int zk_table_compress_dev(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, void* out32_dev) {
     if (!ctx || !t || (!out32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;

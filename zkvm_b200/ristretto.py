@@ -220,6 +220,16 @@ class PointTable:
         self.ctx._check(rc, bad.value)
         return self
 
+    def append_extended(self, ext128) -> "PointTable":
+        """Already-decompressed points as X, Y, Z, T (4 x 32-byte canonical little-endian field elements each)."""
+        h, nb = _as_buf(ext128 if not isinstance(ext128, (list, tuple)) else b"".join(ext128))
+        if nb % 128:
+            raise ValueError("expected a whole number of 128-byte extended points")
+        bad = C.c_size_t(0)
+        rc = self.ctx._lib.zk_table_append_extended(self.ctx._h, self._h, _ptr(h), nb // 128, C.byref(bad))
+        self.ctx._check(rc, bad.value)
+        return self
+
     def append_uniform(self, bytes64) -> "PointTable":
         """RistrettoPoint::from_uniform_bytes over a batch of 64-byte strings."""
         h, nb = _as_buf(bytes64 if not isinstance(bytes64, (list, tuple)) else b"".join(bytes64))
