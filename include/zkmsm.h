@@ -83,6 +83,16 @@ int zk_table_append_uniform_dev(zk_ctx* ctx, zk_table* t, const void* bytes64_de
  * T*Z != X*Y; nothing is appended then. */
 int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index);
 int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index);
+/* Optional, for STATIC generator sets that are multiplied against many times: expand the table into per-window
+ * multiples 2^(c*w) * P (w = 0 .. ceil(253/c)), so that an MSM over it needs no doublings at all and every window shares
+ * one bucket set (fewer additions per point: the width can grow without growing the tree).  Costs W x the memory
+ * (W * 96 B per point) and ~253 doublings + W inversions per point, once.  c = 0 picks the width from the table
+ * length; 4 <= c <= 20 otherwise.  zk_msm_vartime_table / _table_batch / zk_msm_table_dev use the expansion
+ * automatically; appending to the table or clearing it drops it.  Results are bit-identical either way.
+ * (The role dalek's VartimePrecomputedMultiscalarMul plays for static points.) */
+int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c);
+/* Window width of the table's expansion, 0 if it has none. */
+int zk_table_precomputed_window(const zk_table* t);
 /* Encode table[offset .. offset+n) (RFC 9496 4.3.2) into out32 (n*32 bytes). */
 int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, uint8_t* out32_host);
 int zk_table_compress_dev(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, void* out32_dev);

@@ -301,3 +301,33 @@ def test_extended_point_ingestion(ctx, rfc_vectors):
         with pytest.raises(zk.InvalidPoint) as e:
             tt.append_extended(good * 3 + bad + good)
         assert e.value.index == 3 and len(tt) == 0, name
+
+
+def test_precomputed_window_tables(ctx, c_oracle):
+    """A window-expanded static table gives bit-identical results (single, sliced, device-pointer and batched forms)."""
+    import zkvm_b200 as zk
+    n = 5000
+    gens = make_points(c_oracle, n, 77); sc = rand_scalars(n, 77)
+    want = c_oracle.msm(sc, gens, n, threads=4)
+    for c in (0, 4, 9, 16, 20):
+        tab = zk.PointTable(ctx).append_compressed(gens).precompute(c)
+        assert tab.precomputed_window in ((c or 11), (c or 11) - 1)
+        assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want, c
+        off, m = 1234, 2000
+        assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[:m], tab, offset=off)) == \
+            c_oracle.msm(sc[:m], gens[32 * off:32 * (off + m)], m, threads=2), c
+        assert tab.compress() == gens                                       # the plain rows are untouched
+    sizes = [2500, 0, 1, 777, 5000]
+    seg = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    bs = rand_scalars(int(seg[-1]), 78)
+    got = zk.batch_vartime_multiscalar_mul(ctx, bs, tab, seg)
+    for k, (a, b) in enumerate(zip(seg, seg[1:])):
+        a, b = int(a), int(b)
+        assert bytes(got[k]) == c_oracle.msm(bs[a:b], gens[:32 * (b - a)], b - a, threads=2), k
+    # adversarial: every scalar equal -> one bucket holds everything
+    same = bytes(sc[0]) * n
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, same, tab)) == c_oracle.msm(same, gens, n, threads=4)
+    # appending drops the expansion, results stay right
+    tab.append_compressed(gens[:64])
+    assert tab.precomputed_window == 0
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab, n=n)) == want

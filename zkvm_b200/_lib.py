@@ -32,6 +32,8 @@ SYMBOLS = [
     ("zk_table_append_uniform_dev", _i, [_vp, _vp, _vp, _sz]),
     ("zk_table_append_extended", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     ("zk_table_append_extended_dev", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    ("zk_table_precompute", _i, [_vp, _vp, _i]),
+    ("zk_table_precomputed_window", _i, [_vp]),
     ("zk_table_compress", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("zk_table_compress_dev", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("zk_msm_vartime", _i, [_vp, _vp, _vp, _sz, _vp]),

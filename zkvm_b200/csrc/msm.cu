@@ -32,6 +32,19 @@ constexpr int REDUCE_RADIX_LOG2 = 3;               // tree fan-in 8
 constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
 constexpr uint32_t TASK_LEN = 64;                   // longest run of entries one accumulation thread walks
 
+// Window geometry.  A scalar (< 2^253 after reduction) is cut into W signed digits covering 254 bits; the widths are
+// balanced -- the first 254 % W windows are one bit wider than the rest -- so no window is a short stub whose points
+// pile up in a handful of buckets (with a fixed width c, 253 = 19*13 + 6 leaves a 6-bit top window: 64 buckets
+// holding 1/20 of all entries).  The 254th bit is always zero, which absorbs the top digit's carry.
+struct win_geom { int off, width; };
+__host__ __device__ __forceinline__ win_geom window_geom(int W, int w) {
+    int base = 254 / W, extra = 254 % W;
+    win_geom g; g.width = base + (w < extra ? 1 : 0); g.off = w * base + (w < extra ? w : extra);
+    return g;
+}
+static inline int windows_for_width(int c) { return (254 + c - 1) / c; }           // fewest windows of width <= c
+static inline int max_width(int W) { return (254 + W - 1) / W; }
+
 __device__ __forceinline__ void ld_fe(fe& r, const uint4* p) {
     uint4 a = __ldg(p), b = __ldg(p + 1);
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
@@ -179,6 +192,32 @@ __device__ __forceinline__ void niels_to_ext(ge_ext& p, const ge_niels& q) {
     fe_mul(p.T, p.X, p.Y); fe_mul(p.T, p.T, inv2);
 }
 
+// Window expansion of a static table: row w*len + i of the expanded table is the affine-Niels form of 2^(off_w) * P_i.
+// Pass A walks the doubling chain of each point and parks the multiples in extended form; pass B normalises each to
+// Z = 1 (one inversion per entry; this runs once per generator set).
+__global__ void __launch_bounds__(128) k_precomp_double(const uint4* __restrict__ table, size_t len, int W, uint4* __restrict__ scratch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    ge_niels q; ld_niels(q, table, i);
+    ge_ext r; niels_to_ext(r, q);
+#pragma unroll 1
+    for (int w = 1; w < W; w++) {
+#pragma unroll 1
+        for (int d = window_geom(W, w - 1).width; d > 0; d--) ge_dbl(r, r);
+        st_ext(scratch, (size_t)(w - 1) * len + i, r);
+    }
+}
+__global__ void __launch_bounds__(128) k_ext_to_niels(const uint4* __restrict__ ext, size_t n, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p; ld_ext(p, ext, i);
+    fe zi, x, y, t;
+    fe_invert(zi, p.Z);
+    fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi); fe_mul(t, x, y);
+    ge_niels q; ge_to_niels_affine(q, x, y, t);
+    st_niels(out, i, q);
+}
+
 // RFC 9496 4.3.2 over table entries.
 __global__ void __launch_bounds__(128) k_compress_table(const uint4* __restrict__ table, size_t n, uint4* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,35 +252,39 @@ __device__ __forceinline__ void scalar_reduce(uint32_t s[8]) {
     }
 }
 
-// Signed radix-2^c digit w of s (< 2^253), given the carry into this window.  Digits lie in [-2^(c-1), 2^(c-1)].
-__device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c, uint32_t& carry) {
-    int bit = w * c, word = bit >> 5, sh = bit & 31;
+// Signed digit of window g of s, given the carry into it.  Digits lie in [-2^(width-1), 2^(width-1)].
+__device__ __forceinline__ int next_digit(const uint32_t* s, win_geom g, uint32_t& carry) {
+    int word = g.off >> 5, sh = g.off & 31;
     uint32_t lo = word < 8 ? s[word] : 0u, hi = word + 1 < 8 ? s[word + 1] : 0u;
-    uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & ((1u << c) - 1u);
+    uint32_t raw = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & ((1u << g.width) - 1u);
     raw += carry;
-    uint32_t half = 1u << (c - 1);
+    uint32_t half = 1u << (g.width - 1);
     carry = raw > half ? 1u : 0u;
-    return (int)raw - (int)(carry << c);
+    return (int)raw - (int)(carry << g.width);
 }
 
 __global__ void __launch_bounds__(256) k_digit_hist(const uint4* __restrict__ scalars, size_t n, int c, int W,
-                                                    const uint32_t* __restrict__ seg, uint32_t M, uint32_t* __restrict__ counts) {
+                                                    const uint32_t* __restrict__ seg, uint32_t M, uint32_t win_stride,
+                                                    uint32_t* __restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     scalar_reduce(s);
     uint32_t carry = 0; int B = 1 << (c - 1);
-    size_t wbase = seg ? (size_t)segment_of(seg, M, (uint32_t)i) * W : 0;
+    // precomputed-window tables (win_stride != 0): all windows of an MSM share ONE bucket set
+    const int wpm = win_stride ? 1 : W;                  // bucket-space windows per MSM
+    size_t wbase = seg ? (size_t)segment_of(seg, M, (uint32_t)i) * wpm : 0;
     for (int w = 0; w < W; w++) {
-        int d = next_digit(s, w, c, carry);
-        if (d != 0) atomicAdd(&counts[(wbase + w) * B + (abs(d) - 1)], 1u);
+        int d = next_digit(s, window_geom(W, w), carry);
+        if (d != 0) atomicAdd(&counts[(wbase + (win_stride ? 0 : w)) * B + (abs(d) - 1)], 1u);
     }
 }
 
 __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__ scalars, size_t n, int c, int W,
                                                        const uint32_t* __restrict__ seg, uint32_t M, int shared_points,
-                                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+                                                       uint32_t win_stride, uint32_t* __restrict__ cursor,
+                                                       uint32_t* __restrict__ entries) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
@@ -249,7 +292,8 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     scalar_reduce(s);
     uint32_t carry = 0; int B = 1 << (c - 1);
     uint32_t m = seg ? segment_of(seg, M, (uint32_t)i) : 0u;
-    size_t wbase = (size_t)m * W;
+    const int wpm = win_stride ? 1 : W;
+    size_t wbase = (size_t)m * wpm;
     // the point of term i: the i-th point, or (every MSM of the batch runs over the SAME points) the (i - seg[m])-th
     uint32_t pidx = shared_points ? (uint32_t)i - seg[m] : (uint32_t)i;
     // 8 windows at a time: the 8 returning atomics are issued back to back, then the 8 stores
@@ -258,9 +302,10 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             int w = w0 + k;
-            int d = w < W ? next_digit(s, w, c, carry) : 0;
-            val[k] = d != 0 ? (pidx | (d < 0 ? 0x80000000u : 0u)) : 0xffffffffu;
-            pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + w) * B + (abs(d) - 1)], 1u) : 0u;
+            int d = w < W ? next_digit(s, window_geom(W, w), carry) : 0;
+            // precomputed mode: window w of point p is row w*win_stride + p of the expanded table (= 2^(c*w) * P)
+            val[k] = d != 0 ? ((pidx + (uint32_t)w * win_stride) | (d < 0 ? 0x80000000u : 0u)) : 0xffffffffu;
+            pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + (win_stride ? 0 : w)) * B + (abs(d) - 1)], 1u) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
@@ -627,8 +672,9 @@ __global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(cons
     if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
 }
 
-// Horner over the per-window sums: out[m] = sum_w 2^(c*w) * Wt[m*W + w].  One quad per MSM (253 dependent doublings).
-__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int cbits, uint32_t nmsm,
+// Horner over the per-window sums: out[m] = sum_w 2^(off_w) * Wt[m*W + w].  One quad per MSM (253 dependent doublings).
+// `geomW` = number of digit windows the offsets come from (windows == 1 with precomputed tables: nothing to double).
+__global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int geomW, uint32_t nmsm,
                                                        uint4* __restrict__ out_ext) {
     const uint32_t m = blockIdx.x * 8 + (threadIdx.x >> 2);
     if (m >= nmsm) return;
@@ -639,7 +685,7 @@ __global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__
 #pragma unroll 1
     for (int w = windows - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (int d = 0; d < cbits; d++) quad_dbl(acc, acc, c);
+        for (int d = window_geom(geomW, w).width; d > 0; d--) quad_dbl(acc, acc, c);
         quad_ld(tmp, base, w, c.q);
         quad_add(acc, acc, tmp, c);
     }
@@ -759,7 +805,17 @@ struct zk_table {
     int device = 0;
     uint4* d = nullptr;
     size_t len = 0, cap = 0;
+    // optional window expansion (zk_table_precompute): pre[(w*pre_len + i)] = 2^(pre_c*w) * point i, w < pre_W
+    uint4* pre = nullptr;
+    size_t pre_len = 0;
+    int pre_c = 0, pre_W = 0;
 };
+struct Precomp { const uint4* base; uint32_t stride; int c, W; };
+static bool table_precomp(const zk_table* t, size_t offset, size_t n, Precomp* pc) {
+    if (!t->pre || offset + n > t->pre_len) return false;
+    pc->base = t->pre + offset * 6; pc->stride = (uint32_t)t->pre_len; pc->c = t->pre_c; pc->W = t->pre_W;
+    return true;
+}
 
 #define CK(ctx, call)                                                                              \
     do {                                                                                           \
@@ -859,13 +915,12 @@ extern "C" int zk_ctx_last_phase_ms(zk_ctx* ctx, float out_ms[4]) {
 }
 extern "C" uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-// Window width by size.  Measured on B200 (tools/sweep_windows.py, profiles/README.md): the widths whose TOP window is
-// either almost full (c = 15, 16: 13 of 253 bits left over) or carry-only (c = 11: 253 = 23*11) keep the bucket
-// occupancy even across windows; widths in between (12, 13, 14) concentrate the top window's points in a few
-// buckets and lose to them at every size.  Small MSMs are bound by the ~0.45 ms serial tail, so one width serves
-// them all.
+// Window width by size, measured on B200 (tools/sweep_windows.py, profiles/README.md).  Widths are balanced across
+// windows (window_geom), so the curve is smooth in c; small MSMs sit on the ~0.45 ms serial tail and only care about
+// keeping the tree shallow.
 extern "C" int zk_pick_window(size_t n) {
-    if (n < ((size_t)1 << 14)) return 11;
+    if (n < ((size_t)1 << 11)) return 10;
+    if (n < ((size_t)1 << 15)) return 13;
     if (n < ((size_t)1 << 20)) return 15;
     return 16;
 }
@@ -875,7 +930,7 @@ extern "C" int zk_pick_window(size_t n) {
 static int pick_window_batch(size_t n_avg) {
     int best = 4; double best_cost = 1e300;
     for (int c = 4; c <= 16; c++) {
-        double W = 253 / c + 1, B = (double)(1u << (c - 1));
+        double W = windows_for_width(c), B = (double)(1u << (max_width((int)W) - 1));
         double cost = W * (7.0 * (double)(n_avg ? n_avg : 1) + 36.0 * B);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
@@ -903,14 +958,21 @@ extern "C" int zk_table_create(zk_ctx* ctx, size_t capacity, zk_table** out) {
 extern "C" void zk_table_destroy(zk_table* t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    if (t->pre) cudaFree(t->pre);
     if (t->d) cudaFree(t->d);
     delete t;
 }
 extern "C" size_t zk_table_len(const zk_table* t) { return t ? t->len : 0; }
 extern "C" size_t zk_table_capacity(const zk_table* t) { return t ? t->cap : 0; }
-extern "C" void zk_table_clear(zk_table* t) { if (t) t->len = 0; }
+static void table_drop_precomp(zk_table* t) {
+    if (t->pre) { cudaSetDevice(t->device); cudaFree(t->pre); }
+    t->pre = nullptr; t->pre_len = 0; t->pre_c = t->pre_W = 0;
+}
+extern "C" void zk_table_clear(zk_table* t) { if (t) { t->len = 0; table_drop_precomp(t); } }
+extern "C" int zk_table_precomputed_window(const zk_table* t) { return t && t->pre ? t->pre_c : 0; }
 
 static int table_reserve(zk_ctx* ctx, zk_table* t, size_t need) {
+    if (need > t->len) table_drop_precomp(t);       // appending invalidates a window expansion (re-run zk_table_precompute)
     if (need <= t->cap) return ZK_OK;
     size_t cap = t->cap * 2 > need ? t->cap * 2 : need;
     uint4* nd = nullptr;
@@ -972,6 +1034,38 @@ extern "C" int zk_table_append_uniform(zk_ctx* ctx, zk_table* t, const uint8_t* 
     CK(ctx, cudaMemcpyAsync(ctx->comp.p, bytes64_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     return zk_table_append_uniform_dev(ctx, t, ctx->comp.p, n);
 }
+extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
+    if (!ctx || !t || (c != 0 && (c < 4 || c > 20))) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    table_drop_precomp(t);
+    const size_t len = t->len;
+    if (len == 0) return ZK_OK;
+    if (c == 0) {              // about half a point per bucket-window pair keeps the tree small next to the accumulation
+        int lg = 0; while (((size_t)2 << lg) <= len) lg++;
+        c = lg - 1; if (c < 8) c = 8; if (c > 20) c = 20;
+    }
+    const int W = windows_for_width(c);
+    c = max_width(W);
+    if ((unsigned long long)len * W >= (1ull << 31)) return ZK_ERR_ARG;
+    uint4* pre = nullptr; uint4* scratch = nullptr;
+    CK(ctx, cudaMalloc((void**)&pre, len * W * 96));
+    cudaError_t e = cudaMalloc((void**)&scratch, len * (size_t)(W - 1) * 128);
+    if (e != cudaSuccess) { cudaFree(pre); CK(ctx, e); }
+    cudaStream_t st = ctx->stream;
+    e = cudaMemcpyAsync(pre, t->d, len * 96, cudaMemcpyDeviceToDevice, st);             // window 0 = the points themselves
+    if (e == cudaSuccess) {
+        k_precomp_double<<<grid_for(len, 128), 128, 0, st>>>(t->d, len, W, scratch);
+        k_ext_to_niels<<<grid_for(len * (W - 1), 128), 128, 0, st>>>(scratch, len * (size_t)(W - 1), pre + len * 6);
+        ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (e != cudaSuccess) { cudaFree(pre); CK(ctx, e); }
+    t->pre = pre; t->pre_len = len; t->pre_c = c; t->pre_W = W;
+    return ZK_OK;
+}
+
 extern "C" int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index) {
     if (!ctx || !t || (!ext128_dev && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -1019,7 +1113,8 @@ extern "C" int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, 
 // scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
 // Batch mode (nmsm > 1): seg_dev = nmsm+1 offsets in HBM; out_ext_dev receives nmsm extended points.
 static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split, size_t n,
-                        void* out_ext_dev, size_t nmsm = 1, const uint32_t* seg_dev = nullptr, bool shared_points = false) {
+                        void* out_ext_dev, size_t nmsm = 1, const uint32_t* seg_dev = nullptr, bool shared_points = false,
+                        const Precomp* pc = nullptr) {
     cudaStream_t st = ctx->stream;
     if (n == 0) {
         k_set_identity_batch<<<grid_for(nmsm, 128), 128, 0, st>>>((uint4*)out_ext_dev, nmsm);
@@ -1027,9 +1122,14 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         return ZK_OK;
     }
     if (n >= (1ull << 31)) return ZK_ERR_ARG;
-    const int c = ctx->forced_window ? ctx->forced_window : (nmsm > 1 ? pick_window_batch(n / nmsm) : zk_pick_window(n));
-    const int W1 = 253 / c + 1;                 // windows per MSM
-    const size_t W = (size_t)W1 * nmsm;         // windows in the whole batch
+    // precomputed-window table: its width is fixed, every window of an MSM lands in one shared bucket set, no Horner
+    const int c_req = pc ? pc->c : ctx->forced_window ? ctx->forced_window : (nmsm > 1 ? pick_window_batch(n / nmsm) : zk_pick_window(n));
+    const int W1 = pc ? pc->W : windows_for_width(c_req);   // digit windows per scalar (balanced widths, see window_geom)
+    const int c = max_width(W1);                            // widest window -> buckets per window
+    const int WB = pc ? 1 : W1;                 // bucket-space windows per MSM
+    const size_t W = (size_t)WB * nmsm;         // bucket-space windows in the whole batch
+    const uint32_t win_stride = pc ? pc->stride : 0u;
+    if (pc) { tab_a = pc->base; tab_b = pc->base; split = (size_t)0xffffffffu; }
     const size_t B = (size_t)1 << (c - 1);
     const size_t NB = B * W;
     if (NB >= (1ull << 31)) return ZK_ERR_ARG;
@@ -1053,7 +1153,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
     CK(ctx, cudaMemsetAsync(ctx->plan.p, 0, (TASK_LEN + 2) * 4, st));
-    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, (uint32_t*)ctx->counts.p);
+    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, win_stride, (uint32_t*)ctx->counts.p);
     LAUNCH_CHECK(ctx);
     k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (unsigned long long*)ctx->tiles.p,
                                                         (uint32_t*)ctx->plan.p);
@@ -1064,7 +1164,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
                                                     (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->task_off.p,
                                                     (uint32_t*)ctx->plan.p, (uint2*)ctx->tasks.p);
     LAUNCH_CHECK(ctx);
-    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0,
+    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0, win_stride,
                                                        (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -1095,7 +1195,7 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
     }
-    k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, W1, c, (uint32_t)nmsm, (uint4*)out_ext_dev);
+    k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev);
     LAUNCH_CHECK(ctx);
     return ZK_OK;
 }
@@ -1121,7 +1221,9 @@ extern "C" int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk
     if (!ctx || !t || !out_ext128_dev || (!scalars32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     if (ctx->profiling) { CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream)); }
-    return msm_pipeline(ctx, scalars32_dev, t->d + offset * 6, nullptr, n, n, out_ext128_dev);
+    Precomp pc;
+    bool use_pc = table_precomp(t, offset, n, &pc);
+    return msm_pipeline(ctx, scalars32_dev, t->d + offset * 6, nullptr, n, n, out_ext128_dev, 1, nullptr, false, use_pc ? &pc : nullptr);
 }
 
 extern "C" int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]) {
@@ -1140,7 +1242,9 @@ extern "C" int zk_msm_vartime_table(zk_ctx* ctx, const uint8_t* scalars32_host, 
     TRY(ensure(ctx, ctx->out_ext, 128));
     if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    TRY(msm_pipeline(ctx, ctx->scalars.p, t->d + offset * 6, nullptr, n, n, ctx->out_ext.p));
+    Precomp pc;
+    bool use_pc = table_precomp(t, offset, n, &pc);
+    TRY(msm_pipeline(ctx, ctx->scalars.p, t->d + offset * 6, nullptr, n, n, ctx->out_ext.p, 1, nullptr, false, use_pc ? &pc : nullptr));
     if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], ctx->stream));
     return finish_encode(ctx, ctx->out_ext.p, 1, out32);
 }
@@ -1243,7 +1347,9 @@ static int batch_common(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_
         tab = (const uint4*)ctx->dyn_table.p;
     }
     if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, st));
-    TRY(msm_pipeline(ctx, ctx->scalars.p, tab, tab, (size_t)0xffffffffu, n, ctx->batch_ext.p, m, seg_dev, t != nullptr));
+    Precomp pc;
+    bool use_pc = t && table_precomp(t, offset, longest, &pc);
+    TRY(msm_pipeline(ctx, ctx->scalars.p, tab, tab, (size_t)0xffffffffu, n, ctx->batch_ext.p, m, seg_dev, t != nullptr, use_pc ? &pc : nullptr));
     k_encode_batch<<<grid_for(m, 64), 64, 0, st>>>((const uint4*)ctx->batch_ext.p, m, (uint4*)ctx->batch_out.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], st));

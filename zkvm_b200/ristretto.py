@@ -220,6 +220,16 @@ class PointTable:
         self.ctx._check(rc, bad.value)
         return self
 
+    def precompute(self, c: int = 0) -> "PointTable":
+        """Expand a static generator table into per-window multiples (no doublings, shared buckets) -- the device-side
+        counterpart of dalek's VartimePrecomputedMultiscalarMul.  W x the memory; run once per generator set."""
+        self.ctx._check(self.ctx._lib.zk_table_precompute(self.ctx._h, self._h, c))
+        return self
+
+    @property
+    def precomputed_window(self) -> int:
+        return int(self.ctx._lib.zk_table_precomputed_window(self._h))
+
     def append_extended(self, ext128) -> "PointTable":
         """Already-decompressed points as X, Y, Z, T (4 x 32-byte canonical little-endian field elements each)."""
         h, nb = _as_buf(ext128 if not isinstance(ext128, (list, tuple)) else b"".join(ext128))
