@@ -331,3 +331,28 @@ def test_precomputed_window_tables(ctx, c_oracle):
     tab.append_compressed(gens[:64])
     assert tab.precomputed_window == 0
     assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab, n=n)) == want
+
+
+def test_block_scale_2e22_negation_and_split(ctx, c_oracle):
+    """BASELINE config 5's size on one GPU: 2^22 points.  sum s_i P_i + sum (l - s_i) P_i encodes to the identity, and
+    index-range partial sums (the multi-GPU sharding identity) add up to the whole."""
+    import zkvm_b200 as zk
+    n = 1 << 22
+    u = np.random.default_rng(22).integers(0, 256, size=(n // 2, 64), dtype=np.uint8)
+    tab = zk.PointTable(ctx, n).append_uniform(u)
+    tab.append_compressed(tab.compress())                     # the same 2^21 points again: table of 2^22
+    assert len(tab) == n
+    sc = rand_scalars(n // 2, 22)
+    s_int = [int.from_bytes(bytes(r), "little") % L for r in sc]
+    neg = np.frombuffer(b"".join(le32(L - v) for v in s_int), dtype=np.uint8).reshape(-1, 32)
+    both = np.concatenate([sc, neg])
+    assert zk.RistrettoPoint.vartime_multiscalar_mul(ctx, both, tab).is_identity()
+    # positive half only, whole vs 8 shards
+    whole = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab, n=n // 2)
+    assert not whole.is_identity()
+    from zkvm_b200.sharded import shard_range
+    parts = b""
+    for r in range(8):
+        lo, hi = shard_range(n // 2, r, 8)
+        parts += bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[lo:hi], tab, offset=lo))
+    assert c_oracle.point_sum(parts, 8) == bytes(whole)
