@@ -30,6 +30,7 @@ namespace {
 
 constexpr int REDUCE_RADIX_LOG2 = 3;               // tree fan-in 8
 constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
+constexpr size_t TREE_WARP_MAX_NODES = 2048;        // upper tree levels with at most this many nodes use a warp per node
 constexpr uint32_t TASK_LEN = 64;                   // longest run of entries one accumulation thread walks
 
 // Window geometry.  A scalar (< 2^253 after reduction) is cut into W signed digits covering 254 bits; the widths are
@@ -532,6 +533,10 @@ __device__ __forceinline__ void fe_shfl_xor(fe& r, const fe& a, int m, unsigned 
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(mask, a.v[i], m);
 }
+__device__ __forceinline__ void fe_shfl_down(fe& r, const fe& a, int d, unsigned mask) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(mask, a.v[i], d);
+}
 __device__ __forceinline__ void quad_identity(fe& r, int q) { r = fe_zero(); r.v[0] = (q == 1 || q == 2) ? 1u : 0u; }
 // in: lane0 = E, lane1 = H, lane2 = F, lane3 = G.  out: (X3, Y3, Z3, T3) = (E*F, G*H, F*G, E*H) in lanes 0..3.
 __device__ __forceinline__ void quad_finish(fe& r, const fe& val, const quad_ctx& c) {
@@ -670,6 +675,47 @@ __global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(cons
         quad_add(acc, acc, wsum, c);
     }
     if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
+}
+
+// Upper tree levels when there are few nodes: one WARP per node, quad j owning child j.  The 24 dependent additions
+// of the serial recurrence become a 3-step suffix scan plus 3-step butterflies across the quads of the warp
+// (8 + 3*level addition depths instead of 26 + 3*level).  Costs 8x the lanes, so it is only used when the level
+// is latency-bound (see msm_pipeline).
+__global__ void __launch_bounds__(128) k_tree_level_warp(const uint4* __restrict__ a_in, const uint4* __restrict__ wt_in, size_t m_in,
+                                                         size_t m_out, int windows, int log2_wc,
+                                                         uint4* __restrict__ a_out, uint4* __restrict__ wt_out) {
+    const size_t node = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, quad = lane >> 2;
+    quad_ctx c = quad_self(); c.mask = 0xffffffffu;        // every lane of the warp takes part in every step
+    const int q = c.q;
+    const bool active = node < m_out * (size_t)windows;    // warp-uniform
+    size_t w = active ? node / m_out : 0, k = active ? node % m_out : 0;
+    size_t j = k * REDUCE_RADIX + quad;
+    const bool valid = active && j < m_in;
+    fe S, R, Ws, tmp, tmp2, ident;
+    quad_identity(ident, q);
+    if (valid) { quad_ld(S, a_in + w * m_in * 8, j, q); quad_ld(Ws, wt_in + w * m_in * 8, j, q); }
+    else { S = ident; Ws = ident; }
+    // suffix scan over the 8 quads: S_j = sum_{i >= j} A_i
+#pragma unroll 1
+    for (int d = 1; d < 8; d <<= 1) {
+        fe_shfl_down(tmp, S, 4 * d, 0xffffffffu);
+        fe_select(tmp, ident, tmp, quad + d < 8);
+        quad_add(S, S, tmp, c);
+    }
+    // butterflies: R = sum_j S_j = sum_i (i+1) A_i ; Ws = sum_i Wt_i
+    R = S;
+#pragma unroll 1
+    for (int o = 4; o < 32; o <<= 1) {
+        fe_shfl_xor(tmp, R, o, 0xffffffffu); fe_shfl_xor(tmp2, Ws, o, 0xffffffffu);
+        quad_add(R, R, tmp, c); quad_add(Ws, Ws, tmp2, c);
+    }
+    fe run; fe_shfl(run, S, q, 0xffffffffu);               // S_0 = plain sum, from quad 0
+    quad_neg(tmp, run, q); quad_add(R, R, tmp, c);         // sum_i i*A_i
+#pragma unroll 1
+    for (int d = 0; d < log2_wc; d++) quad_dbl(R, R, c);
+    quad_add(R, R, Ws, c);
+    if (active && quad == 0) { quad_st(a_out, node, q, run); quad_st(wt_out, node, q, R); }
 }
 
 // Horner over the per-window sums: out[m] = sum_w 2^(off_w) * Wt[m*W + w].  One quad per MSM (253 dependent doublings).
@@ -1190,7 +1236,10 @@ static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a
         size_t m_out = (m_in + REDUCE_RADIX - 1) / REDUCE_RADIX;
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
-        k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, (int)W, log2_wc, a_out, w_out);
+        if (toff == nullptr && m_out * W <= TREE_WARP_MAX_NODES)      // few nodes: latency-bound, spend lanes on depth
+            k_tree_level_warp<<<grid_for(m_out * W * 32, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, (int)W, log2_wc, a_out, w_out);
+        else
+            k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, (int)W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
