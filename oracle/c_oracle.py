@@ -13,8 +13,8 @@ _lib = None
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "msm_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        # -march=native is decided on the machine that runs it: rebuild there if the .so came from another host
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", _SO, src, "-lpthread"])
+        # x86-64-v3 (AVX2, BMI2, ADX-era servers): the .so is built here and runs on the GPU box, so no -march=native
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-o", _SO, src, "-lpthread"])
     return _SO
 
 

@@ -356,3 +356,67 @@ def test_block_scale_2e22_negation_and_split(ctx, c_oracle):
         lo, hi = shard_range(n // 2, r, 8)
         parts += bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[lo:hi], tab, offset=lo))
     assert c_oracle.point_sum(parts, 8) == bytes(whole)
+
+
+def test_large_2e24_window_independence_and_cancellation(ctx):
+    """A single-GPU MSM well past the headline size (2^24 terms, 16.8 M): two window widths agree, and
+    sum s_i P_i + sum (l - s_i) P_i over the same points encodes to the identity."""
+    import zkvm_b200 as zk
+    n = 1 << 24
+    half = n // 2
+    rng = np.random.default_rng(24)
+    tab = zk.PointTable(ctx, half)
+    for _ in range(4):                                           # 2^23 points, appended in pieces (growth path)
+        tab.append_uniform(rng.integers(0, 256, size=(half // 4, 64), dtype=np.uint8))
+    sc = rng.integers(0, 256, size=(half, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0f                                            # < 2^252 < l, so l - s is the exact negation
+    s_le = sc.view(np.uint64).reshape(half, 4)
+    l_words = np.array([(L >> (64 * k)) & (2**64 - 1) for k in range(4)], dtype=np.uint64)
+    neg = np.zeros_like(s_le); borrow = np.zeros(half, dtype=np.uint64)
+    for k in range(4):                                           # vectorised 256-bit l - s
+        a = np.full(half, l_words[k], dtype=np.uint64); b = s_le[:, k]
+        d = a - b - borrow
+        borrow = ((a < b) | ((a == b) & (borrow == 1))).astype(np.uint64)
+        neg[:, k] = d
+    neg8 = neg.view(np.uint8).reshape(half, 32)
+    r16 = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)
+    ctx.set_window(14)
+    r14 = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)
+    ctx.set_window(0)
+    assert bytes(r16) == bytes(r14) and not r16.is_identity()
+    rneg = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, neg8, tab)
+    # P + (-P) = identity: feed the two 32-byte results back as a 2-term MSM with unit scalars
+    assert zk.RistrettoPoint.optional_multiscalar_mul(ctx, le32(1) * 2, bytes(r16) + bytes(rneg)).is_identity()
+
+
+def test_argument_errors_and_context_reuse(ctx, c_oracle):
+    import zkvm_b200 as zk
+    pts = make_points(c_oracle, 64, 3); sc = rand_scalars(64, 3)
+    with pytest.raises(ValueError):
+        zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc[:10], pts)               # length mismatch
+    with pytest.raises(ValueError):
+        zk.RistrettoPoint.optional_multiscalar_mul(ctx, b"\x00" * 33, pts[:32])      # not a multiple of 32
+    with pytest.raises(zk.ZkError):
+        ctx.set_window(3)
+    with pytest.raises(zk.ZkError):
+        ctx.set_window(17)
+    tab = zk.PointTable(ctx).append_compressed(pts)
+    with pytest.raises(zk.ZkError):
+        zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab, offset=1)            # slice past the end
+    with pytest.raises(ValueError):
+        zk.batch_optional_multiscalar_mul(ctx, sc, pts, [1, 64])                     # segments must start at 0
+    with pytest.raises(zk.ZkError):
+        zk.batch_optional_multiscalar_mul(ctx, sc, pts, [0, 40, 30, 64])             # not ascending
+    # the context is still good after every failure
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == c_oracle.msm(sc, pts, 64)
+    tab.clear()
+    assert len(tab) == 0
+    assert zk.RistrettoPoint.vartime_multiscalar_mul(ctx, b"", tab).is_identity()
+    # two contexts on one device interleave safely
+    c2 = zk.Context(0)
+    t2 = zk.PointTable(c2).append_compressed(pts)
+    for _ in range(3):
+        a = zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)
+        b = zk.RistrettoPoint.vartime_multiscalar_mul(c2, sc, t2)
+        assert bytes(a) == bytes(b)
+    t2.close(); c2.close()
