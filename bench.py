@@ -372,6 +372,25 @@ def run_cuda(a):
                  "msm_per_s_host_api": bm / bt, "ms_host_api": bt * 1e3, "msm_per_s_device": bm / (sum(ph[1:]) * 1e-3),
                  "device_phases_ms": {"digits_sort": ph[1], "bucket_accum": ph[2], "reduce_encode": ph[3]}}
 
+    # ---- extra: single-call latencies at the proof-sized shapes BASELINE.json names (MSM level only) -------------
+    shapes = None
+    if rank == 0 and a.log2n >= 16:
+        def lat(fn, reps=5):
+            fn(); t0 = time.perf_counter()
+            for _ in range(reps): fn()
+            return (time.perf_counter() - t0) / reps * 1e3
+        m16 = 1 << 16
+        gens = zk.PointTable(ctx, m16).append_compressed(np_comp[0][: 32 * m16])
+        s16 = np_scal[0][: 32 * m16]; dyn_s = np_scal[1][: 32 * 64]; dyn_p = np_comp[1][: 32 * 64]
+        shapes = {"what": "host-API latency of one MSM, ms; MSM-level stand-ins for the proof shapes in BASELINE.json configs "
+                          "(the proofs themselves are blocked, SURVEY.md section 0)",
+                  "table_2e16": lat(lambda: zk.RistrettoPoint.vartime_multiscalar_mul(ctx, s16, gens)),
+                  "mixed_2e16_static_plus_64_dynamic": lat(lambda: zk.RistrettoPoint.mixed_multiscalar_mul(ctx, s16, gens, dyn_s, dyn_p)),
+                  "compressed_4096": lat(lambda: zk.RistrettoPoint.optional_multiscalar_mul(ctx, np_scal[0][: 32 * 4096], np_comp[0][: 32 * 4096]))}
+        gens.precompute(0)
+        shapes["table_2e16_precomputed"] = lat(lambda: zk.RistrettoPoint.vartime_multiscalar_mul(ctx, s16, gens))
+        gens.close()
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -412,6 +431,7 @@ def run_cuda(a):
         }
         if batch: out["batch"] = batch
         if precomp: out["precomputed_tables"] = precomp
+        if shapes: out["proof_sized_shapes"] = shapes
         if not a.no_cpu_baseline:
             try:
                 threads = host_threads()

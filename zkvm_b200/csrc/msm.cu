@@ -441,9 +441,6 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
 #ifndef ZK_ACCUM_L2PREFETCH
 #define ZK_ACCUM_L2PREFETCH 1
 #endif
-#ifndef ZK_ACCUM_PREFETCH
-#define ZK_ACCUM_PREFETCH 0
-#endif
 __device__ __forceinline__ void ld_point(ge_niels& q, const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b, uint32_t split, uint32_t e) {
     uint32_t idx = e & 0x7fffffffu;
     if (idx < split) ld_niels(q, tab_a, idx); else ld_niels(q, tab_b, idx - split);
@@ -459,21 +456,6 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
     uint32_t lo = offsets[d.x] + d.y * TASK_LEN, end = offsets[d.x + 1];
     uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
     ge_ext acc;
-#if ZK_ACCUM_PREFETCH
-    ge_identity(acc);
-    // software pipeline: the index two entries ahead and the point one entry ahead are in flight during a madd
-    uint32_t e0 = entries[lo];                       // a task is never empty
-    uint32_t e1 = lo + 1 < hi ? entries[lo + 1] : 0u;
-    ge_niels q; ld_point(q, tab_a, tab_b, split, e0);
-#pragma unroll 1
-    for (uint32_t k = lo; k < hi; k++) {
-        uint32_t e2 = k + 2 < hi ? entries[k + 2] : 0u;
-        ge_niels qn;
-        if (k + 1 < hi) ld_point(qn, tab_a, tab_b, split, e1); else qn = q;
-        ge_madd(acc, acc, q, (e0 >> 31) != 0);
-        q = qn; e0 = e1; e1 = e2;
-    }
-#else
     {   // a task is never empty: start from its first point (1 multiply) instead of identity + point (7)
         uint32_t e = entries[lo];
         ge_niels q; ld_point(q, tab_a, tab_b, split, e);
@@ -502,7 +484,6 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
         ge_niels q; ld_point(q, tab_a, tab_b, split, e);
         ge_madd(acc, acc, q, (e >> 31) != 0);
     }
-#endif
 #endif
     st_ext(partials, task_off[d.x] + d.y, acc);
 }
