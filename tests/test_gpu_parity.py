@@ -311,7 +311,7 @@ def test_precomputed_window_tables(ctx, c_oracle):
     want = c_oracle.msm(sc, gens, n, threads=4)
     for c in (0, 4, 9, 16, 20):
         tab = zk.PointTable(ctx).append_compressed(gens).precompute(c)
-        assert tab.precomputed_window in ((c or 11), (c or 11) - 1)
+        assert tab.precomputed_window in ((c or 13), (c or 13) - 1)
         assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want, c
         off, m = 1234, 2000
         assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc[:m], tab, offset=off)) == \

@@ -1067,9 +1067,9 @@ extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
     table_drop_precomp(t);
     const size_t len = t->len;
     if (len == 0) return ZK_OK;
-    if (c == 0) {              // about half a point per bucket-window pair keeps the tree small next to the accumulation
+    if (c == 0) {              // measured optimum (tools/perf_precomp.py, perf_batch_pre.py): one bit more than log2(len)
         int lg = 0; while (((size_t)2 << lg) <= len) lg++;
-        c = lg - 1; if (c < 8) c = 8; if (c > 20) c = 20;
+        c = lg + 1; if (c < 8) c = 8; if (c > 20) c = 20;
     }
     const int W = windows_for_width(c);
     c = max_width(W);
