@@ -30,6 +30,17 @@ int main(int, char** argv) {
     for (auto b : *r1) printf("%02x", b); printf("\n");
     for (auto b : r2) printf("%02x", b); printf("\n");
     printf("%d\n", (int)RistrettoPoint::is_identity(r2));
+    // window-expanded table, mixed form, and a 3-MSM batch whose pieces cover everything
+    t.precompute(0);
+    auto r3 = RistrettoPoint::vartime_multiscalar_mul(ctx, s, t);
+    for (auto b : r3) printf("%02x", b); printf("\n");
+    std::vector<Scalar> s_st(s.begin(), s.begin() + n / 2), s_dy(s.begin() + n / 2, s.end());
+    std::vector<CompressedRistretto> p_dy(p.begin() + n / 2, p.end());
+    auto r4 = RistrettoPoint::mixed_multiscalar_mul(ctx, s_st, t, 0, s_dy, p_dy);
+    for (auto b : *r4) printf("%02x", b); printf("\n");
+    std::vector<uint64_t> seg = {0, n / 3, n / 3, n};
+    auto rb = RistrettoPoint::batch_optional_multiscalar_mul(ctx, s, p, seg);
+    printf("%d %d\n", (int)rb.size(), (int)RistrettoPoint::is_identity(*rb[1]));
     return 0;
 }
 '''
@@ -48,7 +59,7 @@ def test_cpp_mirror_end_to_end(tmp_path, c_oracle, rfc_vectors):
     blob.write_bytes(np.uint64(n).tobytes() + sc.tobytes() + pts)
     out = subprocess.check_output([str(exe), str(blob)], text=True).split()
     want = c_oracle.msm(sc, pts, n).hex()
-    assert out == [want, want, "0"]
+    assert out == [want, want, "0", want, want, "3", "1"]
     bad = bytearray(pts); bad[32 * 5:32 * 6] = bytes.fromhex(rfc_vectors["bad_encodings"]["negative_s"][2])
     blob.write_bytes(np.uint64(n).tobytes() + sc.tobytes() + bytes(bad))
     assert subprocess.check_output([str(exe), str(blob)], text=True).split() == ["none"]

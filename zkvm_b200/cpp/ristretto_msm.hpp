@@ -57,6 +57,17 @@ class PointTable {
         return std::nullopt;
     }
     void append_uniform(const uint8_t* bytes64, size_t n) { ctx_.check(zk_table_append_uniform(ctx_.raw(), h_, bytes64, n)); }
+    // Already-decompressed points as X, Y, Z, T (4 x 32-byte canonical field elements each); index of the first bad one.
+    std::optional<size_t> append_extended(const uint8_t* ext128, size_t n) {
+        size_t bad = 0;
+        int rc = zk_table_append_extended(ctx_.raw(), h_, ext128, n, &bad);
+        if (rc == ZK_ERR_INVALID_POINT) return bad;
+        ctx_.check(rc);
+        return std::nullopt;
+    }
+    // Window expansion for static generator sets (the device-side VartimePrecomputedMultiscalarMul); c = 0 picks the width.
+    void precompute(int c = 0) { ctx_.check(zk_table_precompute(ctx_.raw(), h_, c)); }
+    int precomputed_window() const { return zk_table_precomputed_window(h_); }
     std::vector<CompressedRistretto> compress(size_t offset, size_t n) const {
         std::vector<CompressedRistretto> out(n);
         ctx_.check(zk_table_compress(ctx_.raw(), h_, offset, n, reinterpret_cast<uint8_t*>(out.data())));
@@ -86,6 +97,44 @@ struct RistrettoPoint {
                                 reinterpret_cast<const uint8_t*>(points.data()), scalars.size(), out.data());
         if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
         ctx.check(rc);
+        return out;
+    }
+    // Cached generators first, then the proof's own compressed points (bulletproofs' verification shape).
+    static std::optional<CompressedRistretto> mixed_multiscalar_mul(Context& ctx, const std::vector<Scalar>& static_scalars,
+                                                                    const PointTable& table, size_t offset,
+                                                                    const std::vector<Scalar>& dyn_scalars,
+                                                                    const std::vector<CompressedRistretto>& dyn_points) {
+        if (dyn_scalars.size() != dyn_points.size()) throw Error(ZK_ERR_ARG, "dynamic scalars/points length mismatch");
+        CompressedRistretto out{};
+        int rc = zk_msm_vartime_mixed(ctx.raw(), reinterpret_cast<const uint8_t*>(static_scalars.data()), table.raw(), offset,
+                                      static_scalars.size(), reinterpret_cast<const uint8_t*>(dyn_scalars.data()),
+                                      reinterpret_cast<const uint8_t*>(dyn_points.data()), dyn_points.size(), out.data());
+        if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
+        ctx.check(rc);
+        return out;
+    }
+    // m independent MSMs in one device pass; MSM k covers terms [seg[k], seg[k+1]).  nullopt where an encoding was invalid.
+    static std::vector<std::optional<CompressedRistretto>> batch_optional_multiscalar_mul(
+        Context& ctx, const std::vector<Scalar>& scalars, const std::vector<CompressedRistretto>& points, const std::vector<uint64_t>& seg) {
+        if (seg.size() < 2 || scalars.size() != points.size() || seg.back() != scalars.size()) throw Error(ZK_ERR_ARG, "bad segments");
+        size_t m = seg.size() - 1;
+        std::vector<CompressedRistretto> out(m); std::vector<uint8_t> valid(m);
+        int rc = zk_msm_vartime_batch(ctx.raw(), reinterpret_cast<const uint8_t*>(scalars.data()),
+                                      reinterpret_cast<const uint8_t*>(points.data()), seg.data(), m,
+                                      reinterpret_cast<uint8_t*>(out.data()), valid.data());
+        if (rc != ZK_OK && rc != ZK_ERR_INVALID_POINT) ctx.check(rc);
+        std::vector<std::optional<CompressedRistretto>> res(m);
+        for (size_t k = 0; k < m; k++) if (valid[k]) res[k] = out[k];
+        return res;
+    }
+    // m MSMs over the SAME cached points (m proofs against one generator set).
+    static std::vector<CompressedRistretto> batch_vartime_multiscalar_mul(Context& ctx, const std::vector<Scalar>& scalars,
+                                                                          const PointTable& table, const std::vector<uint64_t>& seg,
+                                                                          size_t offset = 0) {
+        if (seg.size() < 2 || seg.back() != scalars.size()) throw Error(ZK_ERR_ARG, "bad segments");
+        std::vector<CompressedRistretto> out(seg.size() - 1);
+        ctx.check(zk_msm_vartime_table_batch(ctx.raw(), reinterpret_cast<const uint8_t*>(scalars.data()), table.raw(), offset,
+                                             seg.data(), seg.size() - 1, reinterpret_cast<uint8_t*>(out.data())));
         return out;
     }
     static bool is_identity(const CompressedRistretto& c) { return zk_encoding_is_identity(c.data()) != 0; }
