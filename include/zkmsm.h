@@ -142,7 +142,7 @@ int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8
 int zk_encoding_is_identity(const uint8_t enc32[32]);
 
 /* ---- tuning / measurement ---- */
-/* Force the Pippenger window width (bits, 4..16); 0 restores the size-based choice. */
+/* Force the Pippenger window width (bits, 4..20); 0 restores the size-based choice. */
 int zk_ctx_set_window(zk_ctx* ctx, int c);
 /* Window the size-based rule picks for an n-point MSM. */
 int zk_pick_window(size_t n);

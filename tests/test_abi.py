@@ -39,7 +39,7 @@ def test_host_only_entry_points():
     assert lib.zk_encoding_is_identity(bytes([1]) + bytes(31)) == 0
     assert b"invalid" in lib.zk_status_str(_lib.ZK_ERR_INVALID_POINT)
     for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24):
-        assert 4 <= lib.zk_pick_window(n) <= 16
+        assert 4 <= lib.zk_pick_window(n) <= 20
 
 
 def test_product_never_imports_oracle():

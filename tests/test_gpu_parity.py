@@ -399,7 +399,7 @@ def test_argument_errors_and_context_reuse(ctx, c_oracle):
     with pytest.raises(zk.ZkError):
         ctx.set_window(3)
     with pytest.raises(zk.ZkError):
-        ctx.set_window(17)
+        ctx.set_window(21)
     tab = zk.PointTable(ctx).append_compressed(pts)
     with pytest.raises(zk.ZkError):
         zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab, offset=1)            # slice past the end

@@ -930,7 +930,7 @@ extern "C" int zk_ctx_sync(zk_ctx* ctx) {
 }
 extern "C" void* zk_ctx_stream(zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int zk_ctx_set_window(zk_ctx* ctx, int c) {
-    if (!ctx || (c != 0 && (c < 4 || c > 16))) return ZK_ERR_ARG;
+    if (!ctx || (c != 0 && (c < 4 || c > 20))) return ZK_ERR_ARG;
     ctx->forced_window = c;
     return ZK_OK;
 }
@@ -949,7 +949,10 @@ extern "C" int zk_pick_window(size_t n) {
     if (n < ((size_t)1 << 11)) return 10;
     if (n < ((size_t)1 << 15)) return 13;
     if (n < ((size_t)1 << 20)) return 15;
-    return 16;
+    if (n < ((size_t)1 << 23)) return 16;
+    if (n < ((size_t)1 << 24)) return 18;     // block-scale sizes (tools/big_sweep.py)
+    if (n < ((size_t)1 << 26)) return 19;
+    return 20;
 }
 
 // Batches are throughput-bound (many MSMs hide each other's serial tails), so the width minimises the multiply
