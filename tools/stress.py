@@ -51,4 +51,16 @@ while time.time() < t_end:
         for j, (a, b) in enumerate(zip(seg, seg[1:])):
             a, b = int(a), int(b)
             assert bytes(got[j]) == c_oracle.msm(sc[a:b], pts[32 * a:32 * b], b - a), ("batch", it, n, j)
+    if it % 11 == 0:
+        # m MSMs over one shared (sometimes window-expanded) table
+        m = int(rng.integers(1, 12)); per = int(rng.integers(1, max(2, n // m + 1)))
+        per = min(per, n)
+        seg = np.arange(0, m * per + 1, per, dtype=np.uint64)
+        bs = scalars(m * per)
+        shared = zk.PointTable(ctx).append_compressed(pts[:32 * per])
+        if it % 22 == 0: shared.precompute(int(rng.integers(4, 21)))
+        got = zk.batch_vartime_multiscalar_mul(ctx, bs, shared, seg)
+        for j in range(m):
+            assert bytes(got[j]) == c_oracle.msm(bs[j * per:(j + 1) * per], pts[:32 * per], per), ("table batch", it, j)
+        shared.close()
 print(f"stress ok: {it} iterations in {seconds:.0f} s, seed {seed}")
