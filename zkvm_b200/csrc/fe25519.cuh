@@ -152,10 +152,14 @@ ZK_HD ZK_INLINE bool fe_from_words(fe& r, const uint32_t w[8]) {
     return !high && !ge_p;
 }
 
+#ifndef ZK_SQRN_UNROLL
+#define ZK_SQRN_UNROLL 2   // measured on the decoder: 1.980 (1) / 1.939 (2) / 2.019 (4) ms per 2^20 points
+#endif
+constexpr int kSqrnUnroll = ZK_SQRN_UNROLL;
 ZK_HD ZK_INLINE void fe_sqr_n(fe& r, const fe& a, int n) {
     fe_sqr(r, a);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll kSqrnUnroll
 #endif
     for (int i = 1; i < n; i++) fe_sqr(r, r);
 }
