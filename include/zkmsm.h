@@ -43,8 +43,10 @@ typedef enum zk_status {
 
 typedef struct zk_ctx zk_ctx;     /* per-thread handle: device, stream, reusable workspace */
 typedef struct zk_table zk_table; /* device-resident decompressed point cache (affine Niels, 96 B/point) */
+typedef struct zk_mgpu zk_mgpu;   /* one handle over several GPUs of a box: one zk_ctx + one worker thread per device */
+typedef struct zk_mgpu_table zk_mgpu_table; /* point cache sharded by index range over the devices of a zk_mgpu */
 
-#define ZK_ABI_VERSION 1
+#define ZK_ABI_VERSION 2
 int zk_abi_version(void);
 const char* zk_status_str(int status);
 /* Text of the last CUDA failure seen by this ctx (empty string if none). */
@@ -57,6 +59,19 @@ void zk_ctx_destroy(zk_ctx* ctx);
 int zk_ctx_sync(zk_ctx* ctx);
 /* cudaStream_t of the ctx as an opaque pointer (for CUDA-event timing by the caller). */
 void* zk_ctx_stream(zk_ctx* ctx);
+
+/* ---- host buffers ----
+ * Every `*_host` pointer may be ordinary PAGEABLE memory (a Rust Vec<u8>).  Uploads of 256 KiB or more from pageable
+ * memory go through a pinned staging ring inside the ctx (4 x 4 MiB): the calling thread copies chunk i+1 while the DMA
+ * engine moves chunk i and the device decodes chunk i-1, and the caller's buffer may be reused as soon as the call
+ * returns.  Page-locked sources (cudaHostAlloc / zk_host_register) are detected and copied directly, which is faster:
+ * register long-lived buffers once with zk_host_register().  zk_ctx_set_staging: 0 = auto (default), 1 = never stage
+ * (plain cudaMemcpyAsync, which blocks on pageable sources), 2 = always stage. */
+int zk_host_register(void* ptr, size_t bytes);
+int zk_host_unregister(void* ptr);
+int zk_ctx_set_staging(zk_ctx* ctx, int mode);
+/* Bytes this ctx has moved through its staging ring so far. */
+uint64_t zk_ctx_staged_bytes(const zk_ctx* ctx);
 
 /* ---- point tables: "decompress once, cache on device" ----
  * Stand behind: CompressedRistretto::decompress (RFC 9496 4.3.1), RistrettoPoint::from_uniform_bytes
@@ -79,16 +94,25 @@ int zk_table_append_uniform_dev(zk_ctx* ctx, zk_table* t, const void* bytes64_de
  * little-endian field elements (128 bytes per point; any projective representative with Z != 0).  Stands behind
  * "the caller holds Vec<RistrettoPoint>" (dalek's RistrettoPoint is four field elements; FieldElement::to_bytes
  * gives this form without the inversion + square root a CPU-side compress() would cost).  Normalised to Z = 1 on the
- * device.  ZK_ERR_INVALID_POINT (+ lowest index) for a non-canonical coordinate, Z = 0, an off-curve point or
- * T*Z != X*Y; nothing is appended then. */
+ * device.  Fully validated: ZK_ERR_INVALID_POINT (+ lowest index) for a non-canonical coordinate, Z = 0, an off-curve
+ * point, T*Z != X*Y, or a point outside the even subgroup 2E (ristretto255 = 2E / E[4], RFC 9496 section 3: a point with
+ * an odd 8-torsion component is not the representative of any element); nothing is appended then. */
 int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index);
 int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index);
+/* Same input, for points the caller KNOWS to be valid representatives (values of dalek's RistrettoPoint are by
+ * construction): coordinates are taken modulo p, only Z = 0 is rejected, and the normalisation uses one batched
+ * inversion per 8 points instead of one exponentiation per point (about 7x faster).  Passing anything that is not a
+ * valid representative gives undefined results -- use the checked form for untrusted input. */
+int zk_table_append_extended_unchecked(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index);
+int zk_table_append_extended_unchecked_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index);
 /* Optional, for STATIC generator sets that are multiplied against many times: expand the table into per-window
  * multiples 2^(c*w) * P (w = 0 .. ceil(253/c)), so that an MSM over it needs no doublings at all and every window shares
  * one bucket set (fewer additions per point: the width can grow without growing the tree).  Costs W x the memory
  * (W * 96 B per point) and ~253 doublings + W inversions per point, once.  c = 0 picks the width from the table
  * length; 4 <= c <= 20 otherwise.  zk_msm_vartime_table / _table_batch / zk_msm_table_dev use the expansion
- * automatically; appending to the table or clearing it drops it.  Results are bit-identical either way.
+ * automatically when it pays for the slice at hand (a short slice of a long table takes the plain route; while the
+ * expansion is in use its width overrides zk_ctx_set_window); a successful append to the table, or clearing it, drops
+ * it.  Results are bit-identical either way.
  * (The role dalek's VartimePrecomputedMultiscalarMul plays for static points.) */
 int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c);
 /* Window width of the table's expansion, 0 if it has none. */
@@ -140,6 +164,35 @@ int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk_table* t, 
 int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]);
 /* Is the ristretto255 element the identity?  (the accept test of both verifiers) */
 int zk_encoding_is_identity(const uint8_t enc32[32]);
+
+/* ---- several GPUs behind one call (BASELINE.json config 5: point-range shards + one gather of partial points) ----
+ * devices = g distinct CUDA device ordinals (NULL: 0 .. g-1).  Device r runs the whole pipeline over the index range
+ * [r*n/g, (r+1)*n/g) of the call's terms (remainder spread over the first ranks) and leaves a 128-byte extended partial
+ * in its HBM; the g partials are gathered on devices[0], added and encoded there.  Gather: 0 = g-1 peer copies of
+ * 128 bytes (cudaMemcpyPeerAsync over NVLink; default), 1 = one ncclAllGather on a communicator from ncclCommInitAll
+ * (libnccl.so.2 is loaded at run time; ZK_ERR_CUDA if it cannot be).  A zk_mgpu is not thread-safe: one per thread.
+ * Stand behind the same dalek calls as the single-GPU entry points; results are bit-identical to them. */
+int zk_mgpu_create(const int* devices, int g, zk_mgpu** out);
+void zk_mgpu_destroy(zk_mgpu* mg);
+int zk_mgpu_device_count(const zk_mgpu* mg);
+const char* zk_mgpu_last_error(const zk_mgpu* mg);
+int zk_mgpu_set_gather(zk_mgpu* mg, int mode);
+int zk_mgpu_set_staging(zk_mgpu* mg, int mode);
+uint64_t zk_mgpu_launch_count(const zk_mgpu* mg);
+/* out32 = Encode(sum_i scalars[i] * Decode(points[i])) over all g devices; ZK_ERR_INVALID_POINT <=> None. */
+int zk_mgpu_msm_vartime(zk_mgpu* mg, const uint8_t* scalars32_host, const uint8_t* points32_host, size_t n,
+                        uint8_t out32[32]);
+/* Sharded point cache: every append is cut into g index ranges, device r keeps its range. */
+int zk_mgpu_table_create(zk_mgpu* mg, size_t capacity, zk_mgpu_table** out);
+void zk_mgpu_table_destroy(zk_mgpu_table* t);
+size_t zk_mgpu_table_len(const zk_mgpu_table* t);
+void zk_mgpu_table_clear(zk_mgpu_table* t);
+/* All-or-nothing; *bad_index = lowest failing index of THIS append. */
+int zk_mgpu_table_append_compressed(zk_mgpu_table* t, const uint8_t* points32_host, size_t n, size_t* bad_index);
+int zk_mgpu_table_append_uniform(zk_mgpu_table* t, const uint8_t* bytes64_host, size_t n);
+/* sum_i scalars[i] * table[offset + i], i < n, over all g devices. */
+int zk_mgpu_msm_vartime_table(zk_mgpu* mg, const uint8_t* scalars32_host, const zk_mgpu_table* t, size_t offset,
+                              size_t n, uint8_t out32[32]);
 
 /* ---- tuning / measurement ---- */
 /* Force the Pippenger window width (bits, 4..20); 0 restores the size-based choice. */

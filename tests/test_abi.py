@@ -34,7 +34,7 @@ def test_no_torch_types_in_abi():
 def test_host_only_entry_points():
     from zkvm_b200 import _lib
     lib = _lib.load()
-    assert lib.zk_abi_version() == 1
+    assert lib.zk_abi_version() == 2
     assert lib.zk_encoding_is_identity(bytes(32)) == 1
     assert lib.zk_encoding_is_identity(bytes([1]) + bytes(31)) == 0
     assert b"invalid" in lib.zk_status_str(_lib.ZK_ERR_INVALID_POINT)

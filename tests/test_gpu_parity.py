@@ -217,6 +217,29 @@ def test_sample_of_big_against_oracle(ctx, big, c_oracle):
         c_oracle.msm(sc[5000:5000 + m], comp[32 * 5000:32 * (5000 + m)], m, threads=8)
 
 
+def test_full_2e20_against_oracle(ctx, big, c_oracle):
+    """The headline size compared DIRECTLY with the CPU oracle on identical bytes: table path, compressed path and
+    window-expanded path (the multi-threaded C oracle needs well under a second per 2^20 terms)."""
+    import os
+    import zkvm_b200 as zk
+    n, tab, comp, sc = big
+    want = c_oracle.msm(sc, comp, n, threads=min(32, os.cpu_count() or 1))
+    assert want is not None
+    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want
+    assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, comp)) == want
+    ctx.set_staging(2)                      # the same call with every upload forced through the pinned staging ring
+    try:
+        assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, comp)) == want
+    finally:
+        ctx.set_staging(0)
+    tab.precompute(0)
+    try:
+        assert tab.precomputed_window > 0
+        assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want
+    finally:
+        tab.clear(); tab.append_compressed(comp)
+
+
 # ---------------- batches of independent MSMs ----------------
 def test_batch_matches_individual_msms(ctx, c_oracle, rfc_vectors):
     import zkvm_b200 as zk
@@ -301,6 +324,63 @@ def test_extended_point_ingestion(ctx, rfc_vectors):
         with pytest.raises(zk.InvalidPoint) as e:
             tt.append_extended(good * 3 + bad + good)
         assert e.value.index == 3 and len(tt) == 0, name
+
+
+def test_extended_rejects_points_outside_even_subgroup(ctx, c_oracle):
+    """ristretto255 = 2E / E[4]: a curve point with an odd 8-torsion component represents no element.  The validated
+    ingestion rejects it; the unchecked form is for trusted representatives and agrees with the validated one on them."""
+    import random
+    import zkvm_b200 as zk
+    from oracle import ristretto255_ref as ref
+    rnd = random.Random(11)
+    P, L = ref.P, ref.L
+
+    def smul(k, p):
+        r = ref.Point.identity()
+        while k:
+            if k & 1: r = r + p
+            p = p + p; k >>= 1
+        return r
+
+    def on_curve_point():
+        while True:
+            y = rnd.randrange(P)
+            x2 = (y * y - 1) * pow(ref.D * y * y + 1, P - 2, P) % P
+            x = pow(x2, (P + 3) // 8, P)
+            if x * x % P != x2: x = x * ref.SQRT_M1 % P
+            if x * x % P == x2: return ref.Point(x, y, 1, x * y)
+
+    t8 = None
+    while t8 is None:                                    # a point of exact order 8
+        q = smul(L, on_curve_point())
+        aff = smul(4, q)
+        if aff.X * pow(aff.Z, P - 2, P) % P != 0 or aff.Y * pow(aff.Z, P - 2, P) % P != 1: t8 = q
+
+    def ser(p, lam):
+        return b"".join((v * lam % P).to_bytes(32, "little") for v in (p.X, p.Y, p.Z, p.T))
+
+    good_pts = [on_curve_point().double() for _ in range(12)] + [ref.Point.identity(), ref.Point(0, P - 1, 1, 0), smul(2, t8), smul(6, t8)]
+    good = [ser(p, rnd.getrandbits(200) + 3) for p in good_pts]
+    t = zk.PointTable(ctx).append_extended(b"".join(good))
+    tu = zk.PointTable(ctx).append_extended_unchecked(b"".join(good))
+    assert len(t) == len(good) and t.compress() == tu.compress()
+    assert t.compress() == b"".join(p.encode() for p in good_pts)
+    for k in (1, 3, 5, 7):                               # odd multiples of the order-8 point leave 2E
+        bad = ser(good_pts[0] + smul(k, t8), rnd.getrandbits(200) + 3)
+        tt = zk.PointTable(ctx)
+        with pytest.raises(zk.InvalidPoint) as e:
+            tt.append_extended(good[1] + good[2] + bad + good[3])
+        assert e.value.index == 2 and len(tt) == 0, k
+    tz = zk.PointTable(ctx)
+    with pytest.raises(zk.InvalidPoint) as e:               # the unchecked form still refuses Z = 0
+        tz.append_extended_unchecked(good[0] + b"".join(v.to_bytes(32, "little") for v in (5, 7, 0, 9)) + good[1])
+    assert e.value.index == 1 and len(tz) == 0
+    # bulk: 3000 valid representatives through the batched-inversion path == the decoder's table
+    n = 3000
+    comp = make_points(c_oracle, n, 5150)
+    blob = b"".join(ser(ref.decode(comp[32 * i:32 * i + 32]), rnd.getrandbits(128) + 2) for i in range(0, n, 10))
+    tb = zk.PointTable(ctx).append_extended_unchecked(blob)
+    assert tb.compress() == b"".join(comp[32 * i:32 * i + 32] for i in range(0, n, 10))
 
 
 def test_precomputed_window_tables(ctx, c_oracle):

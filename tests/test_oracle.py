@@ -89,3 +89,47 @@ def test_c_decompress_reports_first_bad_index(c_oracle, rfc_vectors):
     assert idx == 10
     _, idx = c_oracle.decompress(good * 17, 17, threads=2)
     assert idx is None
+
+
+def test_even_subgroup_criterion():
+    """What the CUDA ingestion of extended points relies on (k_from_extended): a curve point lies in the even subgroup
+    2E -- the set ristretto255 representatives are drawn from (RFC 9496 section 3) -- iff Z^2 - Y^2 is a square."""
+    import random
+    from oracle import ristretto255_ref as ref
+    P, L = ref.P, ref.L
+    rnd = random.Random(3)
+
+    def smul(k, p):
+        r = ref.Point.identity()
+        while k:
+            if k & 1: r = r + p
+            p = p + p; k >>= 1
+        return r
+
+    def on_curve_point():
+        while True:
+            y = rnd.randrange(P)
+            x2 = (y * y - 1) * pow(ref.D * y * y + 1, P - 2, P) % P
+            x = pow(x2, (P + 3) // 8, P)
+            if x * x % P != x2: x = x * ref.SQRT_M1 % P
+            if x * x % P == x2: return ref.Point(x, y, 1, x * y)
+
+    def is_square(a):
+        a %= P
+        return a == 0 or pow(a, (P - 1) // 2, P) == 1
+
+    t8 = None
+    while t8 is None:
+        q = smul(L, on_curve_point())
+        q4 = smul(4, q)
+        if q4.X % P != 0: continue                      # (0, -1) has X = 0: q4 must be the order-2 point, q of order 8
+        if (q4.Y - q4.Z) % P != 0: t8 = q
+    for _ in range(25):
+        base = on_curve_point().double()
+        lam = rnd.randrange(1, P)
+        for k in range(8):
+            pt = base + smul(k, t8)
+            pt = ref.Point(pt.X * lam, pt.Y * lam, pt.Z * lam, pt.T * lam)
+            assert is_square(pt.Z * pt.Z - pt.Y * pt.Y) == (k % 2 == 0)
+            if k % 2 == 0:
+                assert pt.encode() == base.encode()     # adding 4-torsion stays in the same ristretto coset

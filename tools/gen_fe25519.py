@@ -218,17 +218,23 @@ def gen_sqr():
 
 
 def main(path):
+    import io, os
     mul, sqr = gen_mul(), gen_sqr()
-    with open(path, "w") as f:
-        f.write("// GENERATED by tools/gen_fe25519.py -- do not edit.\n")
-        f.write("// out = a*b (resp. a*a) mod p, all operands 8x32-bit little-endian limbs, value in [0, 2^256).\n")
-        for name, em, args in (("fe_mul_limbs", mul, "uint32_t* out, const uint32_t* a, const uint32_t* b"),
-                               ("fe_sqr_limbs", sqr, "uint32_t* out, const uint32_t* a")):
-            f.write(f"ZK_HD ZK_INLINE void {name}({args}) {{\n#if defined(__CUDA_ARCH__)\n")
-            f.write("\n".join("  " + l for l in "\n".join(em.dev).split("\n")))
-            f.write("\n#else\n")
-            f.write("\n".join("  " + l for l in "\n".join(em.host).split("\n")))
-            f.write("\n#endif\n}\n\n")
+    f = io.StringIO()
+    f.write("// GENERATED by tools/gen_fe25519.py -- do not edit.\n")
+    f.write("// out = a*b (resp. a*a) mod p, all operands 8x32-bit little-endian limbs, value in [0, 2^256).\n")
+    for name, em, args in (("fe_mul_limbs", mul, "uint32_t* out, const uint32_t* a, const uint32_t* b"),
+                           ("fe_sqr_limbs", sqr, "uint32_t* out, const uint32_t* a")):
+        f.write(f"ZK_HD ZK_INLINE void {name}({args}) {{\n#if defined(__CUDA_ARCH__)\n")
+        f.write("\n".join("  " + l for l in "\n".join(em.dev).split("\n")))
+        f.write("\n#else\n")
+        f.write("\n".join("  " + l for l in "\n".join(em.host).split("\n")))
+        f.write("\n#endif\n}\n\n")
+    text = f.getvalue()
+    # only touch the file when the content changes: its mtime drives the rebuild of every CUDA object
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as out:
+            out.write(text)
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else "zkvm_b200/csrc/fe25519_mul.inc")

@@ -6,8 +6,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# ZKMSM_LIB: developer override used by tools/perf_variants.sh to A/B kernel builds; the default is the in-tree library
-LIB_PATH = os.environ.get("ZKMSM_LIB") or os.path.join(_HERE, "libzkmsm.so")
+LIB_PATH = os.path.join(_HERE, "libzkmsm.so")
+# Developer-only A/B hook (tools/ab_build.sh): a variant build is honoured only when ZKMSM_DEV=1 is ALSO set and the
+# file lives inside this package directory, so a stray environment variable can never redirect the product path.
+if os.environ.get("ZKMSM_DEV") == "1" and os.environ.get("ZKMSM_LIB"):
+    _cand = os.path.abspath(os.environ["ZKMSM_LIB"])
+    if os.path.dirname(_cand) == _HERE and os.path.basename(_cand).startswith("libzkmsm"):
+        LIB_PATH = _cand
 
 ZK_OK, ZK_ERR_CUDA, ZK_ERR_INVALID_POINT, ZK_ERR_ARG, ZK_ERR_NOMEM = 0, -1, -2, -3, -4
 
@@ -50,6 +55,27 @@ SYMBOLS = [
     ("zk_ctx_set_profiling", _i, [_vp, _i]),
     ("zk_ctx_last_phase_ms", _i, [_vp, C.POINTER(C.c_float * 4)]),
     ("zk_ctx_launch_count", C.c_uint64, [_vp]),
+    ("zk_host_register", _i, [_vp, _sz]),
+    ("zk_host_unregister", _i, [_vp]),
+    ("zk_ctx_set_staging", _i, [_vp, _i]),
+    ("zk_ctx_staged_bytes", C.c_uint64, [_vp]),
+    ("zk_table_append_extended_unchecked", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    ("zk_table_append_extended_unchecked_dev", _i, [_vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    ("zk_mgpu_create", _i, [C.POINTER(_i), _i, C.POINTER(_vp)]),
+    ("zk_mgpu_destroy", None, [_vp]),
+    ("zk_mgpu_device_count", _i, [_vp]),
+    ("zk_mgpu_last_error", C.c_char_p, [_vp]),
+    ("zk_mgpu_set_gather", _i, [_vp, _i]),
+    ("zk_mgpu_set_staging", _i, [_vp, _i]),
+    ("zk_mgpu_launch_count", C.c_uint64, [_vp]),
+    ("zk_mgpu_msm_vartime", _i, [_vp, _vp, _vp, _sz, _vp]),
+    ("zk_mgpu_table_create", _i, [_vp, _sz, C.POINTER(_vp)]),
+    ("zk_mgpu_table_destroy", None, [_vp]),
+    ("zk_mgpu_table_len", _sz, [_vp]),
+    ("zk_mgpu_table_clear", None, [_vp]),
+    ("zk_mgpu_table_append_compressed", _i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    ("zk_mgpu_table_append_uniform", _i, [_vp, _vp, _sz]),
+    ("zk_mgpu_msm_vartime_table", _i, [_vp, _vp, _vp, _sz, _sz, _vp]),
 ]
 
 _lib = None
@@ -74,7 +100,7 @@ def load() -> C.CDLL:
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)          # AttributeError here == ABI drift between header and library
         fn.restype, fn.argtypes = res, args
-    if lib.zk_abi_version() != 1:
+    if lib.zk_abi_version() != 2:
         raise ImportError("libzkmsm.so ABI version mismatch")
     _lib = lib
     return lib

@@ -65,6 +65,14 @@ class PointTable {
         ctx_.check(rc);
         return std::nullopt;
     }
+    // Same input for points known to be valid representatives (values of a RistrettoPoint): only Z = 0 is rejected.
+    std::optional<size_t> append_extended_unchecked(const uint8_t* ext128, size_t n) {
+        size_t bad = 0;
+        int rc = zk_table_append_extended_unchecked(ctx_.raw(), h_, ext128, n, &bad);
+        if (rc == ZK_ERR_INVALID_POINT) return bad;
+        ctx_.check(rc);
+        return std::nullopt;
+    }
     // Window expansion for static generator sets (the device-side VartimePrecomputedMultiscalarMul); c = 0 picks the width.
     void precompute(int c = 0) { ctx_.check(zk_table_precompute(ctx_.raw(), h_, c)); }
     int precomputed_window() const { return zk_table_precomputed_window(h_); }
@@ -138,6 +146,61 @@ struct RistrettoPoint {
         return out;
     }
     static bool is_identity(const CompressedRistretto& c) { return zk_encoding_is_identity(c.data()) != 0; }
+};
+
+// Several GPUs of one box behind one call (BASELINE.json config 5): point-range shards, one gather of 128-byte partials.
+class MultiGpu {
+  public:
+    enum class Gather { Peer = 0, Nccl = 1 };
+    explicit MultiGpu(const std::vector<int>& devices, Gather gather = Gather::Peer) {
+        int rc = zk_mgpu_create(devices.data(), (int)devices.size(), &h_);
+        if (rc != ZK_OK) throw Error(rc, std::string("zk_mgpu_create: ") + zk_status_str(rc) + " (no CPU fallback)");
+        if (gather != Gather::Peer) check(zk_mgpu_set_gather(h_, (int)gather));
+    }
+    ~MultiGpu() { zk_mgpu_destroy(h_); }
+    MultiGpu(const MultiGpu&) = delete;
+    MultiGpu& operator=(const MultiGpu&) = delete;
+    zk_mgpu* raw() const { return h_; }
+    int device_count() const { return zk_mgpu_device_count(h_); }
+    void check(int rc) const {
+        if (rc != ZK_OK) throw Error(rc, std::string(zk_status_str(rc)) + ": " + zk_mgpu_last_error(h_));
+    }
+    // sum scalars[i] * decompress(points[i]) over all devices; nullopt if any encoding is invalid
+    std::optional<CompressedRistretto> optional_multiscalar_mul(const Scalar* scalars, const CompressedRistretto* points, size_t n) {
+        CompressedRistretto out{};
+        int rc = zk_mgpu_msm_vartime(h_, reinterpret_cast<const uint8_t*>(scalars), reinterpret_cast<const uint8_t*>(points), n, out.data());
+        if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
+        check(rc);
+        return out;
+    }
+  private:
+    zk_mgpu* h_ = nullptr;
+};
+
+// Vec<RistrettoPoint> sharded by index range over the devices of a MultiGpu.
+class MultiGpuTable {
+  public:
+    MultiGpuTable(MultiGpu& mg, size_t capacity = 0) : mg_(mg) { mg_.check(zk_mgpu_table_create(mg.raw(), capacity, &h_)); }
+    ~MultiGpuTable() { zk_mgpu_table_destroy(h_); }
+    MultiGpuTable(const MultiGpuTable&) = delete;
+    MultiGpuTable& operator=(const MultiGpuTable&) = delete;
+    size_t size() const { return zk_mgpu_table_len(h_); }
+    std::optional<size_t> append_compressed(const CompressedRistretto* pts, size_t n) {
+        size_t bad = 0;
+        int rc = zk_mgpu_table_append_compressed(h_, reinterpret_cast<const uint8_t*>(pts), n, &bad);
+        if (rc == ZK_ERR_INVALID_POINT) return bad;
+        mg_.check(rc);
+        return std::nullopt;
+    }
+    void append_uniform(const uint8_t* bytes64, size_t n) { mg_.check(zk_mgpu_table_append_uniform(h_, bytes64, n)); }
+    CompressedRistretto vartime_multiscalar_mul(const Scalar* scalars, size_t offset, size_t n) {
+        CompressedRistretto out{};
+        mg_.check(zk_mgpu_msm_vartime_table(mg_.raw(), reinterpret_cast<const uint8_t*>(scalars), h_, offset, n, out.data()));
+        return out;
+    }
+  private:
+    MultiGpu& mg_;
+    zk_mgpu_table* h_ = nullptr;
 };
 
 }  // namespace zkvm_b200

@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in
 #endif
 }
 
-// RFC 9496 4.3.4 over a batch of 64-byte strings; normalises to Z = 1 and writes affine-Niels entries.
-__global__ void __launch_bounds__(128) k_from_uniform(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table) {
+// RFC 9496 4.3.4 over a batch of 64-byte strings -> extended points (any Z); k_ext_to_niels normalises them with a
+// batched inversion afterwards (one exponentiation per INV_BATCH points instead of one per point).
+__global__ void __launch_bounds__(128) k_map_uniform(const uint4* __restrict__ in, size_t n, uint4* __restrict__ ext_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t w[16];
@@ -148,18 +149,17 @@ __global__ void __launch_bounds__(128) k_from_uniform(const uint4* __restrict__ 
     }
     ge_ext p;
     ristretto_from_uniform(p, w);
-    fe zi, x, y, t;
-    fe_invert(zi, p.Z);
-    fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi); fe_mul(t, x, y);
-    ge_niels q;
-    ge_to_niels_affine(q, x, y, t);
-    st_niels(table, i, q);
+    st_ext(ext_out, i, p);
 }
 
 // Extended points (X, Y, Z, T as 4 x 32-byte little-endian field elements; any representative, any Z != 0) ->
-// affine-Niels entries.  This is how a caller that already holds decompressed points (dalek `RistrettoPoint` =
-// four field elements) hands them over without compressing them on the CPU.  Rejected (index reported): a
-// non-canonical field encoding, Z = 0, a point off the curve -x^2 + y^2 = 1 + d x^2 y^2, or T*Z != X*Y.
+// affine-Niels entries, fully validated.  This is how a caller that already holds decompressed points (dalek
+// `RistrettoPoint` = four field elements) hands them over without compressing them on the CPU.  Rejected (index
+// reported): a non-canonical field encoding, Z = 0, a point off the curve -x^2 + y^2 = 1 + d x^2 y^2, T*Z != X*Y,
+// or a point outside the even subgroup 2E that ristretto255 representatives live in (RFC 9496 section 3: the group is
+// 2E / E[4]).  Membership test: P in 2E  <=>  Z^2 - Y^2 is a square (checked exhaustively against the big-integer
+// oracle in tests/test_oracle.py); the same inverse square root also yields 1/Z, so validation costs no extra
+// exponentiation over the normalisation.
 __global__ void __launch_bounds__(128) k_from_extended(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
                                                        unsigned long long* __restrict__ bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,11 +171,27 @@ __global__ void __launch_bounds__(128) k_from_extended(const uint4* __restrict__
         uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         ok &= fe_from_words(c[k], w);
     }
-    fe zi, x, y, t, xx, yy, lhs, rhs, tmp, one = fe_one(), dd = fe_d();
-    ok &= !fe_is_zero(c[2]);
-    fe_invert(zi, c[2]);
-    fe_mul(x, c[0], zi); fe_mul(y, c[1], zi); fe_mul(t, x, y);
-    fe_mul(tmp, c[3], zi); ok &= fe_eq(tmp, t);                        // T/Z == (X/Z)(Y/Z)
+    fe zz, yy, u, wv, r, zi, x, y, t, xx, lhs, rhs, tmp, one = fe_one(), dd = fe_d();
+    fe_sqr(zz, c[2]); fe_sqr(yy, c[1]);
+    fe_sub(u, zz, yy);                                              // Z^2 - Y^2
+    const bool z_zero = fe_is_zero(c[2]);
+    const bool u_zero = fe_is_zero(u);
+    fe_mul(wv, u, zz);
+    bool sq = fe_sqrt_ratio_m1(r, one, wv);                         // r^2 = 1 / (u Z^2) when that is a square
+    fe_sqr(zi, r); fe_mul(zi, zi, u); fe_mul(zi, zi, c[2]);         // Z * r^2 * u = 1/Z
+    fe_mul(x, c[0], zi); fe_mul(y, c[1], zi);
+    // y = +-1 (u == 0, so x must be 0): the square-root route degenerates; y = Y/Z is +1 or -1 by comparison
+    fe my; fe_neg(my, one);
+    fe_select(tmp, my, one, fe_eq(c[1], c[2]));
+    fe_select(y, y, tmp, u_zero);
+    fe zero = fe_zero();
+    fe_select(x, x, zero, u_zero);
+    ok &= !z_zero & (sq | u_zero);
+    ok &= !u_zero | fe_is_zero(c[0]);
+    fe_mul(t, x, y);
+    fe_mul(tmp, c[3], zi); fe_select(tmp, tmp, zero, u_zero);
+    ok &= fe_eq(tmp, t);                                             // T/Z == (X/Z)(Y/Z)
+    ok &= !u_zero | fe_is_zero(c[3]);
     fe_sqr(xx, x); fe_sqr(yy, y);
     fe_sub(lhs, yy, xx);
     fe_mul(rhs, xx, yy); fe_mul(rhs, rhs, dd); fe_add(rhs, rhs, one);
@@ -208,15 +224,44 @@ __global__ void __launch_bounds__(128) k_precomp_double(const uint4* __restrict_
         st_ext(scratch, (size_t)(w - 1) * len + i, r);
     }
 }
-__global__ void __launch_bounds__(128) k_ext_to_niels(const uint4* __restrict__ ext, size_t n, uint4* __restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    ge_ext p; ld_ext(p, ext, i);
-    fe zi, x, y, t;
-    fe_invert(zi, p.Z);
-    fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi); fe_mul(t, x, y);
-    ge_niels q; ge_to_niels_affine(q, x, y, t);
-    st_niels(out, i, q);
+// Extended points (any Z != 0) -> affine-Niels entries with Montgomery's batched inversion: a thread owns INV_BATCH
+// points (strided by the thread count, so every load/store is coalesced), multiplies their Z's together, inverts the
+// product once (one ~265-operation exponentiation) and peels the individual inverses off with 3 multiplies per point.
+// Also the whole of zk_table_append_extended_unchecked: caller-provided coordinates are taken modulo p (any 256-bit
+// value is a loose representative) and only Z = 0 is rejected (lowest index -> *bad; that entry becomes the identity).
+constexpr int INV_BATCH = 8;
+__global__ void __launch_bounds__(128) k_ext_to_niels(const uint4* __restrict__ ext, size_t n, uint4* __restrict__ out,
+                                                      unsigned long long* __restrict__ bad) {
+    const size_t T = (n + INV_BATCH - 1) / INV_BATCH;               // threads that own at least one point
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    fe pre[INV_BATCH], z, acc = fe_one();
+#pragma unroll
+    for (int k = 0; k < INV_BATCH; k++) {
+        const size_t i = (size_t)k * T + t;
+        if (i < n) {
+            ld_fe_plain(z, ext + i * 8 + 4);
+            if (fe_is_zero(z)) { z = fe_one(); if (bad) atomicMin(bad, (unsigned long long)i); }
+            fe_mul(acc, acc, z);
+        }
+        pre[k] = acc;
+    }
+    fe inv; fe_invert(inv, acc);
+#pragma unroll
+    for (int k = INV_BATCH - 1; k >= 0; k--) {
+        const size_t i = (size_t)k * T + t;
+        if (i >= n) continue;
+        ge_ext p; ld_ext(p, ext, i);
+        const bool zz = fe_is_zero(p.Z);
+        if (zz) p.Z = fe_one();
+        fe zi, x, y, tt;
+        if (k > 0) fe_mul(zi, inv, pre[k - 1]); else zi = inv;
+        fe_mul(inv, inv, p.Z);
+        fe_mul(x, p.X, zi); fe_mul(y, p.Y, zi); fe_mul(tt, x, y);
+        ge_niels q;
+        if (zz) ge_niels_identity(q); else ge_to_niels_affine(q, x, y, tt);
+        st_niels(out, i, q);
+    }
 }
 
 // RFC 9496 4.3.2 over table entries.
@@ -804,54 +849,9 @@ __global__ void __launch_bounds__(256) k_bench_fe(uint32_t* out, int iters, uint
 // ------------------------------------------------------------------------------------------------
 // host side: context, workspace, pipeline
 // ------------------------------------------------------------------------------------------------
+#include "internal.h"
 
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-};
-
-struct zk_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    char err[256] = {0};
-    int forced_window = 0;
-    int profiling = 0;
-    float phase_ms[4] = {0, 0, 0, 0};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // copy/decode side streams: compressed points are uploaded and decoded in chunks on these two while the
-    // main stream uploads the scalars and sorts digits; the main stream joins them right before the accumulation
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    bool join_aux = false;
-    uint64_t launches = 0;
-    // workspace
-    DevBuf scalars, comp, dyn_table, counts, cursor, offsets, tiles, entries, partials, task_off, tasks, plan, tree_a, tree_w, out_ext, out32, bad, seg, batch_ext, batch_out;
-    uint8_t* h_out = nullptr;               // pinned 64 B: [0,32) encoding, [32,40) bad index
-};
-
-struct zk_table {
-    int device = 0;
-    uint4* d = nullptr;
-    size_t len = 0, cap = 0;
-    // optional window expansion (zk_table_precompute): pre[(w*pre_len + i)] = 2^(pre_c*w) * point i, w < pre_W
-    uint4* pre = nullptr;
-    size_t pre_len = 0;
-    int pre_c = 0, pre_W = 0;
-};
 struct Precomp { const uint4* base; uint32_t stride; int c, W; };
-static bool table_precomp(const zk_table* t, size_t offset, size_t n, Precomp* pc) {
-    if (!t->pre || offset + n > t->pre_len) return false;
-    pc->base = t->pre + offset * 6; pc->stride = (uint32_t)t->pre_len; pc->c = t->pre_c; pc->W = t->pre_W;
-    return true;
-}
-
-#define CK(ctx, call)                                                                              \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-            return e_ == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA;                    \
-        }                                                                                          \
-    } while (0)
 
 #define LAUNCH_CHECK(ctx)            \
     do {                             \
@@ -867,7 +867,6 @@ static int ensure(zk_ctx* ctx, DevBuf& b, size_t bytes) {
     b.cap = cap;
     return ZK_OK;
 }
-#define TRY(x) do { int rc_ = (x); if (rc_ != ZK_OK) return rc_; } while (0)
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
@@ -898,6 +897,7 @@ extern "C" int zk_ctx_create(int device, zk_ctx** out) {
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_out, 64);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         fprintf(stderr, "zkmsm: cannot create context on CUDA device %d: %s (there is no CPU fallback)\n", device,
                 cudaGetErrorString(e));
@@ -912,11 +912,17 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) if (ctx->aux[i]) cudaStreamSynchronize(ctx->aux[i]);
     DevBuf* bufs[] = {&ctx->scalars, &ctx->comp, &ctx->dyn_table, &ctx->counts, &ctx->cursor, &ctx->offsets, &ctx->tiles,
-                      &ctx->entries, &ctx->partials, &ctx->task_off, &ctx->tasks, &ctx->plan, &ctx->tree_a, &ctx->tree_w, &ctx->out_ext, &ctx->out32, &ctx->bad, &ctx->seg, &ctx->batch_ext, &ctx->batch_out};
+                      &ctx->entries, &ctx->partials, &ctx->task_off, &ctx->tasks, &ctx->plan, &ctx->tree_a, &ctx->tree_w,
+                      &ctx->out_ext, &ctx->out32, &ctx->bad, &ctx->seg, &ctx->batch_ext, &ctx->batch_out, &ctx->inv_scratch};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (int i = 0; i < ZK_STAGE_SLOTS; i++) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     for (int i = 0; i < 2; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -941,9 +947,73 @@ extern "C" int zk_ctx_last_phase_ms(zk_ctx* ctx, float out_ms[4]) {
     return ZK_OK;
 }
 extern "C" uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int zk_ctx_set_staging(zk_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return ZK_ERR_ARG;
+    ctx->staging_mode = mode;
+    return ZK_OK;
+}
+extern "C" uint64_t zk_ctx_staged_bytes(const zk_ctx* ctx) { return ctx ? ctx->staged_bytes : 0; }
+
+// Page-lock a caller-owned host buffer so that uploads from it are true asynchronous DMA (what a caller with a
+// long-lived Vec<u8> should do once, instead of paying the staging memcpy on every call).
+extern "C" int zk_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return ZK_ERR_ARG;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA; }
+    return ZK_OK;
+}
+extern "C" int zk_host_unregister(void* ptr) {
+    if (!ptr) return ZK_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return ZK_ERR_CUDA; }
+    return ZK_OK;
+}
+
+// ---- host -> device uploads -------------------------------------------------------------------------------------
+static bool host_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+// Asynchronous on `st` when the source is page-locked; from pageable memory the bytes go through the ctx's pinned
+// ring (the calling thread copies chunk i+1 while chunk i is in flight), so `src` may be reused as soon as this returns.
+static int h2d(zk_ctx* ctx, void* dst, const uint8_t* src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return ZK_OK;
+    const bool stage = ctx->staging_mode == 2 ||
+                       (ctx->staging_mode == 0 && bytes >= ZK_STAGE_MIN_BYTES && host_is_pageable(src));
+    if (!stage) {
+        CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return ZK_OK;
+    }
+    for (size_t off = 0; off < bytes; off += ZK_STAGE_SLOT_BYTES) {
+        const size_t len = bytes - off < ZK_STAGE_SLOT_BYTES ? bytes - off : ZK_STAGE_SLOT_BYTES;
+        const unsigned slot = ctx->stage_next++ % ZK_STAGE_SLOTS;
+        if (!ctx->stage[slot]) {
+            CK(ctx, cudaMallocHost((void**)&ctx->stage[slot], ZK_STAGE_SLOT_BYTES));
+            CK(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[slot], cudaEventDisableTiming));
+        }
+        if (ctx->stage_busy[slot]) CK(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));
+        memcpy(ctx->stage[slot], src + off, len);
+        CK(ctx, cudaMemcpyAsync((uint8_t*)dst + off, ctx->stage[slot], len, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
+        ctx->stage_busy[slot] = true;
+        ctx->staged_bytes += len;
+    }
+    return ZK_OK;
+}
+
+// After a failure between the fork onto the side streams and the join: let everything queued drain, so that no copy
+// still reads the caller's buffers and no decoder still writes ctx->bad when the next call starts.
+static void quiesce(zk_ctx* ctx) {
+    for (int i = 0; i < 2; i++) if (ctx->aux[i]) cudaStreamSynchronize(ctx->aux[i]);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->join_aux = false;
+    cudaGetLastError();
+}
 
 // Window width by size, measured on B200 (tools/sweep_windows.py, profiles/README.md).  Widths are balanced across
-// windows (window_geom), so the curve is smooth in c; small MSMs sit on the ~0.45 ms serial tail and only care about
+// windows (window_geom), so the curve is smooth in c; small MSMs sit on the serial tail and only care about
 // keeping the tree shallow.
 extern "C" int zk_pick_window(size_t n) {
     if (n < ((size_t)1 << 11)) return 10;
@@ -957,17 +1027,22 @@ extern "C" int zk_pick_window(size_t n) {
 
 // Batches are throughput-bound (many MSMs hide each other's serial tails), so the width minimises the multiply
 // count W * (7 n + 36 * 2^(c-1)): n mixed adds per window plus two quad additions per bucket in the tree.
+static double window_cost(double n, int c, bool shared_buckets) {
+    double W = windows_for_width(c), B = (double)(1u << (max_width((int)W) - 1));
+    return W * 7.0 * n + (shared_buckets ? 1.0 : W) * 36.0 * B;
+}
 static int pick_window_batch(size_t n_avg) {
     int best = 4; double best_cost = 1e300;
     for (int c = 4; c <= 16; c++) {
-        double W = windows_for_width(c), B = (double)(1u << (max_width((int)W) - 1));
-        double cost = W * (7.0 * (double)(n_avg ? n_avg : 1) + 36.0 * B);
+        double cost = window_cost((double)(n_avg ? n_avg : 1), c, false);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
 }
 
 // ---- tables ----
+// Thread-safety: a zk_table may be READ by several contexts/threads at once (MSMs over it), but appends, clear,
+// precompute and destroy must not run concurrently with any other use of the same table (they may move its storage).
 extern "C" int zk_table_create(zk_ctx* ctx, size_t capacity, zk_table** out) {
     if (!ctx || !out) return ZK_ERR_ARG;
     *out = nullptr;
@@ -988,6 +1063,7 @@ extern "C" int zk_table_create(zk_ctx* ctx, size_t capacity, zk_table** out) {
 extern "C" void zk_table_destroy(zk_table* t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    cudaDeviceSynchronize();                 // other contexts may still have MSMs over this table in flight
     if (t->pre) cudaFree(t->pre);
     if (t->d) cudaFree(t->d);
     delete t;
@@ -995,34 +1071,33 @@ extern "C" void zk_table_destroy(zk_table* t) {
 extern "C" size_t zk_table_len(const zk_table* t) { return t ? t->len : 0; }
 extern "C" size_t zk_table_capacity(const zk_table* t) { return t ? t->cap : 0; }
 static void table_drop_precomp(zk_table* t) {
-    if (t->pre) { cudaSetDevice(t->device); cudaFree(t->pre); }
+    if (t->pre) { cudaSetDevice(t->device); cudaDeviceSynchronize(); cudaFree(t->pre); }
     t->pre = nullptr; t->pre_len = 0; t->pre_c = t->pre_W = 0;
 }
 extern "C" void zk_table_clear(zk_table* t) { if (t) { t->len = 0; table_drop_precomp(t); } }
 extern "C" int zk_table_precomputed_window(const zk_table* t) { return t && t->pre ? t->pre_c : 0; }
 
+// Room for `need` rows.  Growth moves the storage: work queued by OTHER contexts over the old buffer is drained first
+// (cudaDeviceSynchronize), so a table shared between contexts stays valid for everything already submitted.
 static int table_reserve(zk_ctx* ctx, zk_table* t, size_t need) {
-    if (need > t->len) table_drop_precomp(t);       // appending invalidates a window expansion (re-run zk_table_precompute)
     if (need <= t->cap) return ZK_OK;
     size_t cap = t->cap * 2 > need ? t->cap * 2 : need;
     uint4* nd = nullptr;
     CK(ctx, cudaMalloc((void**)&nd, cap * 96));
-    if (t->len) CK(ctx, cudaMemcpyAsync(nd, t->d, t->len * 96, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && t->len) e = cudaMemcpyAsync(nd, t->d, t->len * 96, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(nd); CK(ctx, e); }
     CK(ctx, cudaFree(t->d));
     t->d = nd; t->cap = cap;
     return ZK_OK;
 }
+// `added` rows were appended and validated: only now does an existing window expansion become stale.
+static void table_commit(zk_table* t, size_t added) {
+    if (added) { table_drop_precomp(t); t->len += added; }
+}
 
-// decompress n encodings at `src_dev` into table rows [dst_row, dst_row+n); returns INVALID_POINT + index on reject.
-static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* table, size_t dst_row, size_t* bad_index, bool sync) {
-    if (n == 0) return ZK_OK;
-    TRY(ensure(ctx, ctx->bad, 8));
-    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
-    k_decompress<<<grid_for(ZK_DEC_PAIR ? (n + 1) / 2 : n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
-                                                             (unsigned long long*)ctx->bad.p, 0ull);
-    LAUNCH_CHECK(ctx);
-    if (!sync) return ZK_OK;
+static int read_bad_index(zk_ctx* ctx, size_t* bad_index) {
     CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
@@ -1030,38 +1105,67 @@ static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* ta
     return ZK_OK;
 }
 
+// Decoder launches are sized in whole waves of the device (4 resident 128-thread CTAs per SM at 106 registers), so
+// that only the last chunk of an upload has a partial tail wave.
+static size_t decode_chunk(const zk_ctx* ctx, size_t n) {
+    if (n <= ((size_t)1 << 16)) return n;
+    const size_t wave = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 4 * 128;
+    size_t waves = (n / 8 + wave / 2) / wave;
+    if (waves < 1) waves = 1;
+    return waves * wave;
+}
+
+// decompress n encodings at `src_dev` into table rows [dst_row, dst_row+n); returns INVALID_POINT + index on reject.
+static int decompress_into(zk_ctx* ctx, const void* src_dev, size_t n, uint4* table, size_t dst_row, size_t* bad_index) {
+    if (n == 0) return ZK_OK;
+    TRY(ensure(ctx, ctx->bad, 8));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
+    k_decompress<<<grid_for(ZK_DEC_PAIR ? (n + 1) / 2 : n, 128), 128, 0, ctx->stream>>>((const uint4*)src_dev, n, table + dst_row * 6,
+                                                             (unsigned long long*)ctx->bad.p, 0ull);
+    LAUNCH_CHECK(ctx);
+    return read_bad_index(ctx, bad_index);
+}
+
 extern "C" int zk_table_append_compressed_dev(zk_ctx* ctx, zk_table* t, const void* points32_dev, size_t n, size_t* bad_index) {
     if (!ctx || !t || (!points32_dev && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(table_reserve(ctx, t, t->len + n));
-    TRY(decompress_into(ctx, points32_dev, n, t->d, t->len, bad_index, true));
-    t->len += n;
+    TRY(decompress_into(ctx, points32_dev, n, t->d, t->len, bad_index));
+    table_commit(t, n);
     return ZK_OK;
 }
 extern "C" int zk_table_append_compressed(zk_ctx* ctx, zk_table* t, const uint8_t* points32_host, size_t n, size_t* bad_index) {
     if (!ctx || !t || (!points32_host && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(ensure(ctx, ctx->comp, n * 32));
-    CK(ctx, cudaMemcpyAsync(ctx->comp.p, points32_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(h2d(ctx, ctx->comp.p, points32_host, n * 32, ctx->stream));
     return zk_table_append_compressed_dev(ctx, t, ctx->comp.p, n, bad_index);
+}
+// ext (n x 128 B in HBM) -> rows [dst_row, dst_row + n) with the batched inversion; `bad` may be null
+static int normalise_into(zk_ctx* ctx, const void* ext_dev, size_t n, uint4* table, size_t dst_row, unsigned long long* bad) {
+    k_ext_to_niels<<<grid_for((n + INV_BATCH - 1) / INV_BATCH, 128), 128, 0, ctx->stream>>>((const uint4*)ext_dev, n, table + dst_row * 6, bad);
+    LAUNCH_CHECK(ctx);
+    return ZK_OK;
 }
 extern "C" int zk_table_append_uniform_dev(zk_ctx* ctx, zk_table* t, const void* bytes64_dev, size_t n) {
     if (!ctx || !t || (!bytes64_dev && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(table_reserve(ctx, t, t->len + n));
     if (n) {
-        k_from_uniform<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)bytes64_dev, n, t->d + t->len * 6);
+        TRY(ensure(ctx, ctx->inv_scratch, n * 128));
+        k_map_uniform<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)bytes64_dev, n, (uint4*)ctx->inv_scratch.p);
         LAUNCH_CHECK(ctx);
+        TRY(normalise_into(ctx, ctx->inv_scratch.p, n, t->d, t->len, nullptr));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    t->len += n;
+    table_commit(t, n);
     return ZK_OK;
 }
 extern "C" int zk_table_append_uniform(zk_ctx* ctx, zk_table* t, const uint8_t* bytes64_host, size_t n) {
     if (!ctx || !t || (!bytes64_host && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(ensure(ctx, ctx->comp, n * 64));
-    CK(ctx, cudaMemcpyAsync(ctx->comp.p, bytes64_host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(h2d(ctx, ctx->comp.p, bytes64_host, n * 64, ctx->stream));
     return zk_table_append_uniform_dev(ctx, t, ctx->comp.p, n);
 }
 extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
@@ -1084,8 +1188,9 @@ extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
     cudaStream_t st = ctx->stream;
     e = cudaMemcpyAsync(pre, t->d, len * 96, cudaMemcpyDeviceToDevice, st);             // window 0 = the points themselves
     if (e == cudaSuccess) {
+        const size_t m = len * (size_t)(W - 1);
         k_precomp_double<<<grid_for(len, 128), 128, 0, st>>>(t->d, len, W, scratch);
-        k_ext_to_niels<<<grid_for(len * (W - 1), 128), 128, 0, st>>>(scratch, len * (size_t)(W - 1), pre + len * 6);
+        k_ext_to_niels<<<grid_for((m + INV_BATCH - 1) / INV_BATCH, 128), 128, 0, st>>>(scratch, m, pre + len * 6, nullptr);
         ctx->launches += 2;
         e = cudaGetLastError();
     }
@@ -1096,29 +1201,42 @@ extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
     return ZK_OK;
 }
 
-extern "C" int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index) {
+static int append_extended_common(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index, bool checked) {
     if (!ctx || !t || (!ext128_dev && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(table_reserve(ctx, t, t->len + n));
     if (n == 0) return ZK_OK;
     TRY(ensure(ctx, ctx->bad, 8));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, ctx->stream));
-    k_from_extended<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)ext128_dev, n, t->d + t->len * 6,
-                                                                (unsigned long long*)ctx->bad.p);
-    LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
-    if (b != ~0ull) { if (bad_index) *bad_index = (size_t)b; return ZK_ERR_INVALID_POINT; }
-    t->len += n;
+    if (checked) {
+        k_from_extended<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint4*)ext128_dev, n, t->d + t->len * 6,
+                                                                    (unsigned long long*)ctx->bad.p);
+        LAUNCH_CHECK(ctx);
+    } else {
+        TRY(normalise_into(ctx, ext128_dev, n, t->d, t->len, (unsigned long long*)ctx->bad.p));
+    }
+    TRY(read_bad_index(ctx, bad_index));
+    table_commit(t, n);
     return ZK_OK;
 }
-extern "C" int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index) {
+extern "C" int zk_table_append_extended_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index) {
+    return append_extended_common(ctx, t, ext128_dev, n, bad_index, true);
+}
+extern "C" int zk_table_append_extended_unchecked_dev(zk_ctx* ctx, zk_table* t, const void* ext128_dev, size_t n, size_t* bad_index) {
+    return append_extended_common(ctx, t, ext128_dev, n, bad_index, false);
+}
+static int append_extended_host(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index, bool checked) {
     if (!ctx || !t || (!ext128_host && n)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(ensure(ctx, ctx->comp, n * 128));
-    CK(ctx, cudaMemcpyAsync(ctx->comp.p, ext128_host, n * 128, cudaMemcpyHostToDevice, ctx->stream));
-    return zk_table_append_extended_dev(ctx, t, ctx->comp.p, n, bad_index);
+    TRY(h2d(ctx, ctx->comp.p, ext128_host, n * 128, ctx->stream));
+    return append_extended_common(ctx, t, ctx->comp.p, n, bad_index, checked);
+}
+extern "C" int zk_table_append_extended(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index) {
+    return append_extended_host(ctx, t, ext128_host, n, bad_index, true);
+}
+extern "C" int zk_table_append_extended_unchecked(zk_ctx* ctx, zk_table* t, const uint8_t* ext128_host, size_t n, size_t* bad_index) {
+    return append_extended_host(ctx, t, ext128_host, n, bad_index, false);
 }
 extern "C" int zk_table_compress_dev(zk_ctx* ctx, const zk_table* t, size_t offset, size_t n, void* out32_dev) {
     if (!ctx || !t || (!out32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
@@ -1140,45 +1258,77 @@ extern "C" int zk_table_compress(zk_ctx* ctx, const zk_table* t, size_t offset, 
 }
 
 // ---- the MSM pipeline (asynchronous on ctx->stream) ----
+// A plan fixes the geometry of one pass and makes sure the workspace exists.  It is computed BEFORE anything is
+// queued on the side streams, so that an argument or out-of-memory failure never leaves copies or decoders in flight.
+struct MsmPlan {
+    size_t n = 0, nmsm = 1;
+    int W1 = 0, c = 0, WB = 0;           // digit windows per scalar, widest window, bucket-space windows per MSM
+    size_t W = 0, B = 0, NB = 0, ntiles = 0, max_tasks = 0, m1 = 0;
+    bool use_pc = false; Precomp pc{};
+};
+
+// Does the window expansion pay for an n-term MSM?  Its width was chosen for the whole table; a short slice of a long
+// table would sweep 2^(pre_c - 1) buckets for a handful of entries, so compare the multiply counts of both routes.
+static bool precomp_pays(size_t n, int pre_c) {
+    return window_cost((double)n, pre_c, true) <= window_cost((double)n, zk_pick_window(n), false);
+}
+static bool table_precomp(const zk_table* t, size_t offset, size_t n, Precomp* pc) {
+    if (!t->pre || offset + n > t->pre_len || !precomp_pays(n, t->pre_c)) return false;
+    pc->base = t->pre + offset * 6; pc->stride = (uint32_t)t->pre_len; pc->c = t->pre_c; pc->W = t->pre_W;
+    return true;
+}
+
+static int msm_plan(zk_ctx* ctx, size_t n, size_t nmsm, const Precomp* pc, MsmPlan* p) {
+    p->n = n; p->nmsm = nmsm; p->use_pc = pc != nullptr;
+    if (pc) p->pc = *pc;
+    if (n == 0) return ZK_OK;
+    if (n >= (1ull << 31)) return ZK_ERR_ARG;
+    // precomputed-window table: its width is fixed, every window of an MSM lands in one shared bucket set, no Horner
+    const int c_req = pc ? pc->c : ctx->forced_window ? ctx->forced_window : (nmsm > 1 ? pick_window_batch(n / nmsm) : zk_pick_window(n));
+    p->W1 = pc ? pc->W : windows_for_width(c_req);   // digit windows per scalar (balanced widths, see window_geom)
+    p->c = max_width(p->W1);                           // widest window -> buckets per window
+    p->WB = pc ? 1 : p->W1;
+    p->W = (size_t)p->WB * nmsm;                       // bucket-space windows in the whole batch
+    p->B = (size_t)1 << (p->c - 1);
+    p->NB = p->B * p->W;
+    if (p->NB >= (1ull << 31)) return ZK_ERR_ARG;
+    p->ntiles = (p->NB + 1023) / 1024;
+    if ((unsigned long long)n * p->W1 >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
+    p->max_tasks = p->NB + (n * (size_t)p->W1) / TASK_LEN;
+    p->m1 = (p->B + REDUCE_RADIX - 1) / REDUCE_RADIX;
+    TRY(ensure(ctx, ctx->counts, p->NB * 4));
+    TRY(ensure(ctx, ctx->cursor, p->NB * 4));
+    TRY(ensure(ctx, ctx->offsets, (p->NB + 1) * 4));
+    TRY(ensure(ctx, ctx->task_off, (p->NB + 1) * 4));
+    TRY(ensure(ctx, ctx->tiles, p->ntiles * 8));
+    TRY(ensure(ctx, ctx->plan, (TASK_LEN + 2) * 4));
+    TRY(ensure(ctx, ctx->tasks, p->max_tasks * 8));
+    TRY(ensure(ctx, ctx->entries, n * p->W1 * 4));
+    TRY(ensure(ctx, ctx->partials, p->max_tasks * 128));
+    TRY(ensure(ctx, ctx->tree_a, 2 * p->m1 * p->W * 128));     // ping-pong halves
+    TRY(ensure(ctx, ctx->tree_w, 2 * p->m1 * p->W * 128));
+    return ZK_OK;
+}
+
 // scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
 // Batch mode (nmsm > 1): seg_dev = nmsm+1 offsets in HBM; out_ext_dev receives nmsm extended points.
-static int msm_pipeline(zk_ctx* ctx, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split, size_t n,
-                        void* out_ext_dev, size_t nmsm = 1, const uint32_t* seg_dev = nullptr, bool shared_points = false,
-                        const Precomp* pc = nullptr) {
+static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split,
+                       void* out_ext_dev, const uint32_t* seg_dev = nullptr, bool shared_points = false) {
     cudaStream_t st = ctx->stream;
+    const size_t n = p.n, nmsm = p.nmsm;
     if (n == 0) {
+        if (ctx->join_aux) {
+            for (int i = 0; i < 2; i++) CK(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+            ctx->join_aux = false;
+        }
         k_set_identity_batch<<<grid_for(nmsm, 128), 128, 0, st>>>((uint4*)out_ext_dev, nmsm);
         LAUNCH_CHECK(ctx);
         return ZK_OK;
     }
-    if (n >= (1ull << 31)) return ZK_ERR_ARG;
-    // precomputed-window table: its width is fixed, every window of an MSM lands in one shared bucket set, no Horner
-    const int c_req = pc ? pc->c : ctx->forced_window ? ctx->forced_window : (nmsm > 1 ? pick_window_batch(n / nmsm) : zk_pick_window(n));
-    const int W1 = pc ? pc->W : windows_for_width(c_req);   // digit windows per scalar (balanced widths, see window_geom)
-    const int c = max_width(W1);                            // widest window -> buckets per window
-    const int WB = pc ? 1 : W1;                 // bucket-space windows per MSM
-    const size_t W = (size_t)WB * nmsm;         // bucket-space windows in the whole batch
-    const uint32_t win_stride = pc ? pc->stride : 0u;
-    if (pc) { tab_a = pc->base; tab_b = pc->base; split = (size_t)0xffffffffu; }
-    const size_t B = (size_t)1 << (c - 1);
-    const size_t NB = B * W;
-    if (NB >= (1ull << 31)) return ZK_ERR_ARG;
-    const size_t ntiles = (NB + 1023) / 1024;
-
-    if ((unsigned long long)n * W1 >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
-    const size_t max_tasks = NB + (n * (size_t)W1) / TASK_LEN;
-    TRY(ensure(ctx, ctx->counts, NB * 4));
-    TRY(ensure(ctx, ctx->cursor, NB * 4));
-    TRY(ensure(ctx, ctx->offsets, (NB + 1) * 4));
-    TRY(ensure(ctx, ctx->task_off, (NB + 1) * 4));
-    TRY(ensure(ctx, ctx->tiles, ntiles * 8));
-    TRY(ensure(ctx, ctx->plan, (TASK_LEN + 2) * 4));
-    TRY(ensure(ctx, ctx->tasks, max_tasks * 8));
-    TRY(ensure(ctx, ctx->entries, n * W1 * 4));
-    TRY(ensure(ctx, ctx->partials, max_tasks * 128));
-    size_t m1 = (B + REDUCE_RADIX - 1) / REDUCE_RADIX;
-    TRY(ensure(ctx, ctx->tree_a, 2 * m1 * W * 128));     // ping-pong halves
-    TRY(ensure(ctx, ctx->tree_w, 2 * m1 * W * 128));
+    const int W1 = p.W1, c = p.c, WB = p.WB;
+    const size_t W = p.W, B = p.B, NB = p.NB, ntiles = p.ntiles, max_tasks = p.max_tasks, m1 = p.m1;
+    const uint32_t win_stride = p.use_pc ? p.pc.stride : 0u;
+    if (p.use_pc) { tab_a = p.pc.base; tab_b = p.pc.base; split = (size_t)0xffffffffu; }
 
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
@@ -1253,10 +1403,12 @@ static int finish_encode(zk_ctx* ctx, const void* ext_dev, size_t g, uint8_t out
 extern "C" int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk_table* t, size_t offset, size_t n, void* out_ext128_dev) {
     if (!ctx || !t || !out_ext128_dev || (!scalars32_dev && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
-    if (ctx->profiling) { CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream)); }
     Precomp pc;
-    bool use_pc = table_precomp(t, offset, n, &pc);
-    return msm_pipeline(ctx, scalars32_dev, t->d + offset * 6, nullptr, n, n, out_ext128_dev, 1, nullptr, false, use_pc ? &pc : nullptr);
+    const bool use_pc = table_precomp(t, offset, n, &pc);
+    MsmPlan plan;
+    TRY(msm_plan(ctx, n, 1, use_pc ? &pc : nullptr, &plan));
+    if (ctx->profiling) { CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream)); }
+    return msm_enqueue(ctx, plan, scalars32_dev, t->d + offset * 6, nullptr, n, out_ext128_dev);
 }
 
 extern "C" int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]) {
@@ -1268,52 +1420,40 @@ extern "C" int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size
     return rc;
 }
 
-extern "C" int zk_msm_vartime_table(zk_ctx* ctx, const uint8_t* scalars32_host, const zk_table* t, size_t offset, size_t n, uint8_t out32[32]) {
-    if (!ctx || !t || !out32 || (!scalars32_host && n) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
-    CK(ctx, cudaSetDevice(ctx->device));
-    TRY(ensure(ctx, ctx->scalars, n * 32));
-    TRY(ensure(ctx, ctx->out_ext, 128));
-    if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    Precomp pc;
-    bool use_pc = table_precomp(t, offset, n, &pc);
-    TRY(msm_pipeline(ctx, ctx->scalars.p, t->d + offset * 6, nullptr, n, n, ctx->out_ext.p, 1, nullptr, false, use_pc ? &pc : nullptr));
-    if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], ctx->stream));
-    return finish_encode(ctx, ctx->out_ext.p, 1, out32);
-}
-
 // Upload n compressed points from the host and decode them into ctx->dyn_table, in chunks alternating between the
 // two side streams so that the copy of chunk i+1 overlaps the decode of chunk i.  The main stream is free to upload
-// scalars and sort digits meanwhile; msm_pipeline() joins the side streams right before the accumulation.
+// scalars and sort digits meanwhile; msm_enqueue() joins the side streams right before the accumulation.
 // ctx->bad (lowest rejected index) must have been reset on the main stream.  Batch mode: seg/M/bad_msm mark the MSM.
 static int start_upload_decode(zk_ctx* ctx, const uint8_t* points32_host, size_t n, const uint32_t* seg_dev, uint32_t M,
                                uint32_t* bad_msm_dev) {
     if (n == 0) return ZK_OK;
     cudaStream_t st = ctx->stream;
     CK(ctx, cudaEventRecord(ctx->ev_fork, st));
-    const size_t chunk = n > (1u << 16) ? (n + 7) / 8 : n;
+    const size_t chunk = decode_chunk(ctx, n);
     int which = 0;
+    ctx->join_aux = true;          // from here on an error return must quiesce() the side streams
     for (size_t lo = 0; lo < n; lo += chunk, which ^= 1) {
         size_t cnt = n - lo < chunk ? n - lo : chunk;
         cudaStream_t sa = ctx->aux[which];
         if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
-        CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->comp.p + lo * 32, points32_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sa));
+        TRY(h2d(ctx, (uint8_t*)ctx->comp.p + lo * 32, points32_host + lo * 32, cnt * 32, sa));
         k_decompress<<<grid_for(ZK_DEC_PAIR ? (cnt + 1) / 2 : cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
                                                         (unsigned long long*)ctx->bad.p, (unsigned long long)lo, seg_dev, M, bad_msm_dev);
         LAUNCH_CHECK(ctx);
     }
     for (int i = 0; i < 2; i++) CK(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
-    ctx->join_aux = true;
     return ZK_OK;
 }
 
-extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32_host, const zk_table* t, size_t offset, size_t n_static,
-                                    const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, uint8_t out32[32]) {
-    if (!ctx || !out32) return ZK_ERR_ARG;
-    if (n_static && (!t || !scalars_static32_host || offset > t->len || n_static > t->len - offset)) return ZK_ERR_ARG;
-    if (n_dyn && (!scalars_dyn32_host || !points_dyn32_host)) return ZK_ERR_ARG;
-    CK(ctx, cudaSetDevice(ctx->device));
-    size_t n = n_static + n_dyn;
+// Everything of a mixed (static table prefix + dynamic compressed suffix) MSM up to the extended result in
+// ctx->out_ext and the reject index in ctx->h_out[32..40): queued, not waited for.
+static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
+                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn) {
+    const size_t n = n_static + n_dyn;
+    Precomp pc;
+    const bool use_pc = n_dyn == 0 && n_static && table_precomp(t, offset, n_static, &pc);
+    MsmPlan plan;
+    TRY(msm_plan(ctx, n, 1, use_pc ? &pc : nullptr, &plan));
     TRY(ensure(ctx, ctx->scalars, n * 32));
     TRY(ensure(ctx, ctx->out_ext, 128));
     TRY(ensure(ctx, ctx->comp, n_dyn * 32));
@@ -1323,16 +1463,57 @@ extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], st));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
     TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
-    if (n_static) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars_static32_host, n_static * 32, cudaMemcpyHostToDevice, st));
-    if (n_dyn) CK(ctx, cudaMemcpyAsync((uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, cudaMemcpyHostToDevice, st));
+    size_t pos = 0;
+    for (int k = 0; k < npieces; k++) {
+        TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + pos, pieces[k].host, pieces[k].bytes, st));
+        pos += pieces[k].bytes;
+    }
+    TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
-    TRY(msm_pipeline(ctx, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, n, ctx->out_ext.p));
+    TRY(msm_enqueue(ctx, plan, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, ctx->out_ext.p));
     if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], st));
     CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));    // after the join inside the pipeline
-    TRY(finish_encode(ctx, ctx->out_ext.p, 1, out32));
+    return ZK_OK;
+}
+
+int zk_internal_enqueue_partial(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
+                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn) {
+    if (!ctx) return ZK_ERR_ARG;
+    size_t sb = 0;
+    for (int k = 0; k < npieces; k++) { if (pieces[k].bytes && !pieces[k].host) return ZK_ERR_ARG; sb += pieces[k].bytes; }
+    if (sb != n_static * 32) return ZK_ERR_ARG;
+    if (n_static && (!t || offset > t->len || n_static > t->len - offset)) return ZK_ERR_ARG;
+    if (n_dyn && (!scalars_dyn32_host || !points_dyn32_host)) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = enqueue_partial_impl(ctx, pieces, npieces, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn);
+    if (rc != ZK_OK) quiesce(ctx);
+    return rc;
+}
+void* zk_internal_partial_ptr(zk_ctx* ctx) { return ctx->out_ext.p; }
+int zk_internal_finish_partial(zk_ctx* ctx, size_t* bad_index) {
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
+    if (bad_index) *bad_index = b == ~0ull ? (size_t)-1 : (size_t)b;
+    return b == ~0ull ? ZK_OK : ZK_ERR_INVALID_POINT;
+}
+
+extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32_host, const zk_table* t, size_t offset, size_t n_static,
+                                    const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, uint8_t out32[32]) {
+    if (!ctx || !out32) return ZK_ERR_ARG;
+    if (n_static && !scalars_static32_host) return ZK_ERR_ARG;
+    zk_host_piece piece = {scalars_static32_host, n_static * 32};
+    TRY(zk_internal_enqueue_partial(ctx, &piece, 1, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn));
+    int rc = finish_encode(ctx, ctx->out_ext.p, 1, out32);
+    if (rc != ZK_OK) { quiesce(ctx); return rc; }
     unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
     if (n_dyn && b != ~0ull) { memset(out32, 0, 32); return ZK_ERR_INVALID_POINT; }
     return ZK_OK;
+}
+
+extern "C" int zk_msm_vartime_table(zk_ctx* ctx, const uint8_t* scalars32_host, const zk_table* t, size_t offset, size_t n, uint8_t out32[32]) {
+    if (!t) return ZK_ERR_ARG;
+    return zk_msm_vartime_mixed(ctx, scalars32_host, t, offset, n, nullptr, nullptr, 0, out32);
 }
 
 extern "C" int zk_msm_vartime(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, size_t n, uint8_t out32[32]) {
@@ -1340,6 +1521,59 @@ extern "C" int zk_msm_vartime(zk_ctx* ctx, const uint8_t* scalars32_host, const 
 }
 
 // ---- batches of independent MSMs -------------------------------------------------------------------
+static int batch_impl(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, const zk_table* t, size_t offset,
+                      const uint64_t* seg_offsets, size_t m, size_t n, size_t longest, uint8_t* out32s, uint8_t* valid,
+                      uint32_t* h_seg, uint32_t* h_bad) {
+    cudaStream_t st = ctx->stream;
+    Precomp pc;
+    const bool use_pc = t && table_precomp(t, offset, longest, &pc);
+    MsmPlan plan;
+    TRY(msm_plan(ctx, n, m, use_pc ? &pc : nullptr, &plan));
+    TRY(ensure(ctx, ctx->scalars, n * 32));
+    TRY(ensure(ctx, ctx->seg, (m + 1) * 4 + m * 4));          // offsets, then per-MSM reject flags
+    TRY(ensure(ctx, ctx->batch_ext, m * 128));
+    TRY(ensure(ctx, ctx->batch_out, m * 32));
+    TRY(ensure(ctx, ctx->bad, 8));
+    if (!t) {
+        TRY(ensure(ctx, ctx->comp, n * 32));
+        TRY(ensure(ctx, ctx->dyn_table, n * 96));
+    }
+    for (size_t i = 0; i <= m; i++) h_seg[i] = (uint32_t)seg_offsets[i];
+    uint32_t* seg_dev = (uint32_t*)ctx->seg.p;
+    uint32_t* bad_msm_dev = seg_dev + (m + 1);
+    CK(ctx, cudaMemcpyAsync(seg_dev, h_seg, (m + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaStreamSynchronize(st));                       // h_seg is pageable: the copy is done before anything forks
+    CK(ctx, cudaMemsetAsync(bad_msm_dev, 0, m * 4, st));
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
+    const uint4* tab;
+    if (t) tab = t->d + offset * 6;
+    else {
+        TRY(start_upload_decode(ctx, points32_host, n, seg_dev, (uint32_t)m, bad_msm_dev));
+        tab = (const uint4*)ctx->dyn_table.p;
+    }
+    TRY(h2d(ctx, ctx->scalars.p, scalars32_host, n * 32, st));
+    TRY(msm_enqueue(ctx, plan, ctx->scalars.p, tab, tab, (size_t)0xffffffffu, ctx->batch_ext.p, seg_dev, t != nullptr));
+    k_encode_batch<<<grid_for(m, 64), 64, 0, st>>>((const uint4*)ctx->batch_ext.p, m, (uint4*)ctx->batch_out.p);
+    LAUNCH_CHECK(ctx);
+    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], st));
+    CK(ctx, cudaMemcpyAsync(out32s, ctx->batch_out.p, m * 32, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(h_bad, bad_msm_dev, m * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (ctx->profiling) {
+        for (int i = 1; i < 4; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
+        }
+        ctx->phase_ms[0] = 0;
+    }
+    int rc = ZK_OK;
+    for (size_t i = 0; i < m; i++) {
+        if (h_bad[i]) { memset(out32s + 32 * i, 0, 32); rc = ZK_ERR_INVALID_POINT; }
+        if (valid) valid[i] = h_bad[i] ? 0 : 1;
+    }
+    return rc;
+}
+
 static int batch_common(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t* points32_host, const zk_table* t, size_t offset,
                         const uint64_t* seg_offsets, size_t m, uint8_t* out32s, uint8_t* valid) {
     if (!ctx || !seg_offsets || !out32s || m == 0 || seg_offsets[0] != 0) return ZK_ERR_ARG;
@@ -1354,59 +1588,12 @@ static int batch_common(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_
     if (n && !scalars32_host) return ZK_ERR_ARG;
     if (t ? (offset > t->len || longest > t->len - offset) : (n && !points32_host)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    TRY(ensure(ctx, ctx->scalars, n * 32));
-    TRY(ensure(ctx, ctx->seg, (m + 1) * 4 + m * 4));          // offsets, then per-MSM reject flags
-    TRY(ensure(ctx, ctx->batch_ext, m * 128));
-    TRY(ensure(ctx, ctx->batch_out, m * 32));
-    TRY(ensure(ctx, ctx->bad, 8));
     uint32_t* h_seg = (uint32_t*)malloc((m + 1) * 4);
-    if (!h_seg) return ZK_ERR_NOMEM;
-    for (size_t i = 0; i <= m; i++) h_seg[i] = (uint32_t)seg_offsets[i];
-    uint32_t* seg_dev = (uint32_t*)ctx->seg.p;
-    uint32_t* bad_msm_dev = seg_dev + (m + 1);
-    cudaError_t e = cudaMemcpyAsync(seg_dev, h_seg, (m + 1) * 4, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // h_seg is pageable: finish the copy before freeing it
-    free(h_seg);
-    CK(ctx, e);
-    CK(ctx, cudaMemsetAsync(bad_msm_dev, 0, m * 4, st));
-    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
-    const uint4* tab;
-    if (t) tab = t->d + offset * 6;
-    else {
-        TRY(ensure(ctx, ctx->comp, n * 32));
-        TRY(ensure(ctx, ctx->dyn_table, n * 96));
-        TRY(start_upload_decode(ctx, points32_host, n, seg_dev, (uint32_t)m, bad_msm_dev));
-        tab = (const uint4*)ctx->dyn_table.p;
-    }
-    if (n) CK(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars32_host, n * 32, cudaMemcpyHostToDevice, st));
-    Precomp pc;
-    bool use_pc = t && table_precomp(t, offset, longest, &pc);
-    TRY(msm_pipeline(ctx, ctx->scalars.p, tab, tab, (size_t)0xffffffffu, n, ctx->batch_ext.p, m, seg_dev, t != nullptr, use_pc ? &pc : nullptr));
-    k_encode_batch<<<grid_for(m, 64), 64, 0, st>>>((const uint4*)ctx->batch_ext.p, m, (uint4*)ctx->batch_out.p);
-    LAUNCH_CHECK(ctx);
-    if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], st));
-    CK(ctx, cudaMemcpyAsync(out32s, ctx->batch_out.p, m * 32, cudaMemcpyDeviceToHost, st));
     uint32_t* h_bad = (uint32_t*)calloc(m, 4);
-    if (!h_bad) return ZK_ERR_NOMEM;
-    e = cudaMemcpyAsync(h_bad, bad_msm_dev, m * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    int rc = ZK_OK;
-    if (e == cudaSuccess && ctx->profiling) {
-        for (int i = 1; i < 4; i++) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
-        }
-        ctx->phase_ms[0] = 0;
-    }
-    if (e == cudaSuccess) {
-        for (size_t i = 0; i < m; i++) {
-            if (h_bad[i]) { memset(out32s + 32 * i, 0, 32); rc = ZK_ERR_INVALID_POINT; }
-            if (valid) valid[i] = h_bad[i] ? 0 : 1;
-        }
-    }
-    free(h_bad);
-    CK(ctx, e);
+    int rc = (h_seg && h_bad) ? batch_impl(ctx, scalars32_host, points32_host, t, offset, seg_offsets, m, n, longest, out32s, valid, h_seg, h_bad)
+                              : ZK_ERR_NOMEM;
+    if (rc != ZK_OK && rc != ZK_ERR_INVALID_POINT) quiesce(ctx);    // nothing may still be reading h_seg / writing h_bad
+    free(h_seg); free(h_bad);
     return rc;
 }
 
@@ -1431,9 +1618,7 @@ extern "C" int zk_bench_int_pipe(zk_ctx* ctx, int kind, double* ops_per_sec) {
     if (!ctx || !ops_per_sec || kind < 0 || kind > 3) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     TRY(ensure(ctx, ctx->out32, 32));
-    int dev_sms = 0;
-    CK(ctx, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    const int blocks = dev_sms * 8, threads = 256;
+    const int blocks = (ctx->sm_count > 0 ? ctx->sm_count : 148) * 8, threads = 256;
     const int iters = kind <= 1 ? 4096 : 512;
     double per_thread = kind == 0 ? 8.0 * iters : kind == 1 ? 8.0 * iters : 2.0 * iters;
     cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];

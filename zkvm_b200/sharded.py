@@ -5,8 +5,13 @@ shard_range(n, r, G), computes one partial sum on its own GPU (no data-path coll
 partial points -- 128 bytes each, extended coordinates -- are gathered with a single NCCL collective;
 rank 0 adds them and encodes.  The gather is latency-bound (G*128 bytes), not bandwidth-bound.
 
-The compute backend is injected so that the host logic (partitioning, gather order, combine) can be
-tested with gloo on CPU; the product backend is `CudaBackend`, which goes through the C ABI.
+Two front ends:
+* `msm_single_process(...)`: ONE process drives all GPUs through the C ABI's zk_mgpu_* entry points (what a Rust
+  verifier calls; partials gathered by peer copies or one ncclAllGather inside the library).  This module only
+  forwards to it.
+* `sharded_msm(...)`: one process per GPU under torch.distributed (how bench.py's scaling runs are launched); the
+  compute backend is injected so that the host logic (partitioning, gather order, combine) can be tested with gloo
+  on CPU; the product backend is `CudaBackend`, which goes through the C ABI.
 """
 from __future__ import annotations
 
@@ -69,3 +74,19 @@ def sharded_msm(backend: Backend, local_scalars: torch.Tensor, n_total: int, gro
     gathered = torch.empty(world, PARTIAL_BYTES, dtype=torch.uint8, device=backend.device)
     dist.all_gather_into_tensor(gathered, part.view(1, PARTIAL_BYTES), group=group)
     return backend.combine(gathered) if rank == 0 else None
+
+
+def msm_single_process(scalars, points, devices=None, g: Optional[int] = None, gather: str = "peer", mg=None) -> Optional[bytes]:
+    """One process, several GPUs: forwards to zk_mgpu_msm_vartime (include/zkmsm.h).  `scalars` / `points` are host
+    buffers of n x 32 bytes (compressed encodings).  Returns the 32-byte encoding, or None for an invalid encoding.
+    Pass a long-lived `mg` (zkvm_b200.MultiGpu) to amortise context creation."""
+    from .ristretto import MultiGpu
+    own = mg is None
+    if own:
+        mg = MultiGpu(devices=devices, g=g, gather=gather)
+    try:
+        r = mg.optional_multiscalar_mul(scalars, points)
+        return None if r is None else bytes(r)
+    finally:
+        if own:
+            mg.close()
