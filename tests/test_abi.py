@@ -61,3 +61,31 @@ def test_context_fails_loudly_without_gpu():
     with pytest.raises(zk.ZkError) as e:
         zk.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_rust_sys_matches_header():
+    """The pre-staged (uncompiled: no rustc in this image) zkmsm-sys crate declares exactly the header's functions, with
+    the same arity and the same pointer/integer class per parameter as the ctypes table the built library is bound with."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys as g
+    from zkvm_b200 import _lib
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0
+    funcs = g.parse_header()
+    assert sorted(f[0] for f in funcs) == header_functions()
+    rs = open(os.path.join(ROOT, "rust", "zkmsm-sys", "src", "lib.rs")).read()
+    decl = dict((m.group(1), m.group(2)) for m in re.finditer(r"pub fn (zk_[a-z0-9_]+)\(([^)]*)\)", rs))
+    assert sorted(decl) == header_functions()
+    table = {n: (res, args) for n, res, args in _lib.SYMBOLS}
+    for name, ret, params in funcs:
+        rust_params = [p for p in decl[name].split(",") if p.strip()]
+        assert len(rust_params) == len(params) == len(table[name][1]), name
+        for (ctype, _), rp, ct in zip(params, rust_params, table[name][1]):
+            is_ptr_c = "*" in ctype
+            is_ptr_rs = "*const" in rp or "*mut" in rp
+            is_ptr_ct = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "_type_") and isinstance(ct._type_, type)
+            assert is_ptr_c == is_ptr_rs == bool(is_ptr_ct), (name, ctype, rp, ct)
+            if not is_ptr_c:
+                size = {"c_int": 4, "usize": 8, "u64": 8, "f32": 4, "f64": 8}[rp.split(":")[1].strip()]
+                assert C.sizeof(ct) == size, (name, ctype, rp)
