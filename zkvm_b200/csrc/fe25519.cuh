@@ -164,6 +164,31 @@ ZK_HD ZK_INLINE void fe_sqr_n(fe& r, const fe& a, int n) {
     for (int i = 1; i < n; i++) fe_sqr(r, r);
 }
 
+// Operation policies.  The throughput kernels inline every multiply (fe_ops_inline).  The single-warp tail kernels
+// (window Horner, final Encode) execute a long stretch of straight-line field code exactly once: fully inlined it is
+// hundreds of KB of SASS and the warp stalls on instruction fetch ("no_instruction" was the top stall of
+// k_ext_sum_encode in round 1); fe_ops_call routes multiplies and squarings through three real functions instead, so
+// the cold path is a few KB that stays in the instruction cache.
+struct fe_ops_inline {
+    static ZK_HD ZK_INLINE void mul(fe& r, const fe& a, const fe& b) { fe_mul(r, a, b); }
+    static ZK_HD ZK_INLINE void sqr(fe& r, const fe& a) { fe_sqr(r, a); }
+    static ZK_HD ZK_INLINE void sqr_n(fe& r, const fe& a, int n) { fe_sqr_n(r, a, n); }
+};
+#if defined(__CUDACC__)
+// by value: 16 operand registers in, 8 out -- no stack traffic across the call
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) { fe r; fe_mul(r, a, b); return r; }
+static __device__ __noinline__ fe fe_sqr_n_call(fe a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) fe_sqr(a, a);
+    return a;
+}
+struct fe_ops_call {
+    static __device__ __forceinline__ void mul(fe& r, const fe& a, const fe& b) { r = fe_mul_call(a, b); }
+    static __device__ __forceinline__ void sqr(fe& r, const fe& a) { r = fe_sqr_n_call(a, 1); }
+    static __device__ __forceinline__ void sqr_n(fe& r, const fe& a, int n) { r = fe_sqr_n_call(a, n); }
+};
+#endif
+
 // Two field elements advanced in lockstep: the exponentiation chains below are 250 dependent squarings, so running
 // two of them interleaved doubles the instruction-level parallelism a thread offers the IMAD pipe.
 struct fe2 { fe a, b; };
@@ -205,6 +230,33 @@ ZK_HD inline void fe_pow22523_t(F& r, const F& z) {
     fe_mul(r, t0, z);              // 2^252-3
 }
 ZK_HD inline void fe_pow22523(fe& r, const fe& z) { fe_pow22523_t<fe>(r, z); }
+// Same ladder through an operation policy (see fe_ops_call).
+template <class Ops>
+ZK_HD inline void fe_pow22523_ops(fe& r, const fe& z) {
+    fe t0, t1, t2;
+    Ops::sqr(t0, z);
+    Ops::sqr_n(t1, t0, 2);
+    Ops::mul(t1, z, t1);
+    Ops::mul(t0, t0, t1);
+    Ops::sqr(t0, t0);
+    Ops::mul(t0, t1, t0);            // 2^5-1
+    Ops::sqr_n(t1, t0, 5);
+    Ops::mul(t0, t1, t0);            // 2^10-1
+    Ops::sqr_n(t1, t0, 10);
+    Ops::mul(t1, t1, t0);            // 2^20-1
+    Ops::sqr_n(t2, t1, 20);
+    Ops::mul(t1, t2, t1);            // 2^40-1
+    Ops::sqr_n(t1, t1, 10);
+    Ops::mul(t0, t1, t0);            // 2^50-1
+    Ops::sqr_n(t1, t0, 50);
+    Ops::mul(t1, t1, t0);            // 2^100-1
+    Ops::sqr_n(t2, t1, 100);
+    Ops::mul(t1, t2, t1);            // 2^200-1
+    Ops::sqr_n(t1, t1, 50);
+    Ops::mul(t0, t1, t0);            // 2^250-1
+    Ops::sqr_n(t0, t0, 2);           // 2^252-4
+    Ops::mul(r, t0, z);              // 2^252-3
+}
 
 // r = a^(p-2) = a^(2^255-21).
 ZK_HD inline void fe_invert(fe& r, const fe& z) {
@@ -219,23 +271,25 @@ ZK_HD inline void fe_invert(fe& r, const fe& z) {
 // RFC 9496 section 4.2 SQRT_RATIO_M1(u, v): returns was_square, r = |sqrt(u/v)| or |sqrt(i*u/v)|.
 // Split around the exponentiation so that two instances can share one interleaved chain.
 struct sqrt_ratio_state { fe v3, t; };
+template <class Ops = fe_ops_inline>
 ZK_HD ZK_INLINE void fe_sqrt_ratio_pre(sqrt_ratio_state& st, const fe& u, const fe& v) {
     fe v7;
-    fe_sqr(st.v3, v); fe_mul(st.v3, st.v3, v);          // v^3
-    fe_sqr(v7, st.v3); fe_mul(v7, v7, v);               // v^7
-    fe_mul(st.t, u, v7);                                // the value to raise to (p-5)/8
+    Ops::sqr(st.v3, v); Ops::mul(st.v3, st.v3, v);          // v^3
+    Ops::sqr(v7, st.v3); Ops::mul(v7, v7, v);               // v^7
+    Ops::mul(st.t, u, v7);                                  // the value to raise to (p-5)/8
 }
+template <class Ops = fe_ops_inline>
 ZK_HD ZK_INLINE bool fe_sqrt_ratio_post(fe& r, const sqrt_ratio_state& st, const fe& powed, const fe& u, const fe& v) {
     fe t, check, nu, nui;
-    fe_mul(t, powed, st.v3); fe_mul(t, t, u);           // r = u v^3 (u v^7)^((p-5)/8)
-    fe_sqr(check, t); fe_mul(check, check, v);          // v r^2
+    Ops::mul(t, powed, st.v3); Ops::mul(t, t, u);           // r = u v^3 (u v^7)^((p-5)/8)
+    Ops::sqr(check, t); Ops::mul(check, check, v);          // v r^2
     fe_neg(nu, u);
     fe i = fe_sqrt_m1();
-    fe_mul(nui, nu, i);
+    Ops::mul(nui, nu, i);
     bool correct = fe_eq(check, u);
     bool flipped = fe_eq(check, nu);
     bool flipped_i = fe_eq(check, nui);
-    fe ri; fe_mul(ri, t, i);
+    fe ri; Ops::mul(ri, t, i);
     fe_select(t, t, ri, flipped | flipped_i);
     fe_abs(r, t);
     return correct | flipped;
@@ -245,6 +299,13 @@ ZK_HD inline bool fe_sqrt_ratio_m1(fe& r, const fe& u, const fe& v) {
     fe_sqrt_ratio_pre(st, u, v);
     fe_pow22523(p, st.t);
     return fe_sqrt_ratio_post(r, st, p, u, v);
+}
+template <class Ops>
+ZK_HD inline bool fe_sqrt_ratio_m1_ops(fe& r, const fe& u, const fe& v) {
+    sqrt_ratio_state st; fe p;
+    fe_sqrt_ratio_pre<Ops>(st, u, v);
+    fe_pow22523_ops<Ops>(p, st.t);
+    return fe_sqrt_ratio_post<Ops>(r, st, p, u, v);
 }
 
 }  // namespace zk

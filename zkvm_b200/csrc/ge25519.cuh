@@ -140,32 +140,35 @@ ZK_HD inline void ristretto_decode_x2(fe& x0, fe& y0, fe& t0, bool& ok0, const u
     ok1 = ristretto_decode_post(x1, y1, t1, d1, isr1, sq1);
 }
 
-// RFC 9496 4.3.2 Encode.  Output: canonical 8 little-endian words.
-ZK_HD inline void ristretto_encode(uint32_t out[8], const ge_ext& p) {
+// RFC 9496 4.3.2 Encode.  Output: canonical 8 little-endian words.  Ops = operation policy (fe_ops_inline in the
+// throughput kernels, fe_ops_call in the single-warp tail).
+template <class Ops>
+ZK_HD inline void ristretto_encode_ops(uint32_t out[8], const ge_ext& p) {
     fe u1, u2, t0, t1, isr, den1, den2, zinv, ix0, iy0, ench, x, y, dinv, one = fe_one();
-    fe_add(t0, p.Z, p.Y); fe_sub(t1, p.Z, p.Y); fe_mul(u1, t0, t1);
-    fe_mul(u2, p.X, p.Y);
-    fe_sqr(t0, u2); fe_mul(t0, t0, u1);
-    fe_sqrt_ratio_m1(isr, one, t0);
-    fe_mul(den1, isr, u1);
-    fe_mul(den2, isr, u2);
-    fe_mul(zinv, den1, den2); fe_mul(zinv, zinv, p.T);
+    fe_add(t0, p.Z, p.Y); fe_sub(t1, p.Z, p.Y); Ops::mul(u1, t0, t1);
+    Ops::mul(u2, p.X, p.Y);
+    Ops::sqr(t0, u2); Ops::mul(t0, t0, u1);
+    fe_sqrt_ratio_m1_ops<Ops>(isr, one, t0);
+    Ops::mul(den1, isr, u1);
+    Ops::mul(den2, isr, u2);
+    Ops::mul(zinv, den1, den2); Ops::mul(zinv, zinv, p.T);
     fe i = fe_sqrt_m1();
-    fe_mul(ix0, p.X, i); fe_mul(iy0, p.Y, i);
+    Ops::mul(ix0, p.X, i); Ops::mul(iy0, p.Y, i);
     fe k = fe_invsqrt_a_minus_d();
-    fe_mul(ench, den1, k);
-    fe_mul(t0, p.T, zinv);
+    Ops::mul(ench, den1, k);
+    Ops::mul(t0, p.T, zinv);
     bool rotate = fe_is_negative(t0);
     fe_select(x, p.X, iy0, rotate);
     fe_select(y, p.Y, ix0, rotate);
     fe_select(dinv, den2, ench, rotate);
-    fe_mul(t0, x, zinv);
+    Ops::mul(t0, x, zinv);
     fe_cneg(y, y, fe_is_negative(t0));
-    fe_sub(t0, p.Z, y); fe_mul(t0, t0, dinv);
+    fe_sub(t0, p.Z, y); Ops::mul(t0, t0, dinv);
     fe_abs(t0, t0);
     fe_freeze(t0, t0);
     for (int j = 0; j < 8; j++) out[j] = t0.v[j];
 }
+ZK_HD inline void ristretto_encode(uint32_t out[8], const ge_ext& p) { ristretto_encode_ops<fe_ops_inline>(out, p); }
 
 // RFC 9496 4.3.4 MAP (Elligator 2 on the Jacobi quartic), t already reduced.
 ZK_HD inline void ristretto_map(ge_ext& r, const fe& t) {

@@ -16,7 +16,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "../../include/zkmsm.h"
 #include "ge25519.cuh"
@@ -779,16 +782,45 @@ __global__ void k_set_identity_batch(uint4* __restrict__ out_ext, size_t m) {
     ge_ext p; ge_identity(p); st_ext(out_ext, i, p);
 }
 
-// out32 = Encode(sum of g extended points)
+// out32 = Encode(sum of g extended points).  One thread; the straight-line field code goes through fe_ops_call so that
+// it stays in the instruction cache (see fe25519.cuh).
 __global__ void k_ext_sum_encode(const uint4* __restrict__ ext, size_t g, uint4* __restrict__ out32) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_ext acc, tmp;
-    ge_identity(acc);
+    ld_ext(acc, ext, 0);
 #pragma unroll 1
-    for (size_t i = 0; i < g; i++) { ld_ext(tmp, ext, i); ge_add(acc, acc, tmp); }
-    uint32_t o[8]; ristretto_encode(o, acc);
+    for (size_t i = 1; i < g; i++) { ld_ext(tmp, ext, i); ge_add(acc, acc, tmp); }
+    uint32_t o[8]; ristretto_encode_ops<fe_ops_call>(o, acc);
     out32[0] = make_uint4(o[0], o[1], o[2], o[3]);
     out32[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// Single-MSM tail in ONE launch: Horner over the window sums (one quad), then RFC 9496 Encode (one thread) -- the
+// extended result is also left in out_ext for callers that want it.  Saves a kernel boundary on the serial tail.
+__global__ void __launch_bounds__(32) k_combine_encode(const uint4* __restrict__ wt, int windows, int geomW,
+                                                       uint4* __restrict__ out_ext, uint4* __restrict__ out32) {
+    __shared__ uint4 sh[8];
+    if (threadIdx.x < 4) {
+        const quad_ctx c = quad_self();
+        fe acc, tmp;
+        quad_ld(acc, wt, windows - 1, c.q);
+#pragma unroll 1
+        for (int w = windows - 2; w >= 0; w--) {
+#pragma unroll 1
+            for (int d = window_geom(geomW, w).width; d > 0; d--) quad_dbl(acc, acc, c);
+            quad_ld(tmp, wt, w, c.q);
+            quad_add(acc, acc, tmp, c);
+        }
+        quad_st(sh, 0, c.q, acc);
+        quad_st(out_ext, 0, c.q, acc);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        ge_ext p; ld_ext(p, sh, 0);
+        uint32_t o[8]; ristretto_encode_ops<fe_ops_call>(o, p);
+        out32[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        out32[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
 }
 
 // ---- integer-pipe microbenchmarks ---------------------------------------------------------------
@@ -976,6 +1008,73 @@ static bool host_is_pageable(const void* p) {
     if (e != cudaSuccess) { cudaGetLastError(); return true; }
     return a.type == cudaMemoryTypeUnregistered;
 }
+
+// A few process-wide helper threads that share the staging memcpy()s with the calling thread: one core copies at
+// ~10 GB/s, a x16 Gen5 link moves ~55 GB/s, so a single-threaded staging copy would be the bottleneck of an upload.
+namespace {
+struct CopyPool {
+    static constexpr int MAX_HELPERS = 3;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    struct Job { uint8_t* dst; const uint8_t* src; size_t len; };
+    Job jobs[MAX_HELPERS];
+    int pending[MAX_HELPERS] = {0, 0, 0};      // 1 = posted, 2 = running
+    uint64_t ticket = 0;
+    std::thread th[MAX_HELPERS];
+    int nhelpers = 0;
+    bool started = false, quit = false;
+    std::mutex user_mu;                         // one striped copy at a time (callers from several threads queue up)
+    void start() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (started) return;
+        started = true;
+        unsigned hw = std::thread::hardware_concurrency();
+        nhelpers = hw >= 16 ? 3 : hw >= 8 ? 2 : hw >= 4 ? 1 : 0;
+        for (int i = 0; i < nhelpers; i++) th[i] = std::thread([this, i] { run(i); });
+    }
+    void run(int i) {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return pending[i] == 1 || quit; });
+            if (quit) return;
+            Job j = jobs[i]; pending[i] = 2;
+            lk.unlock();
+            memcpy(j.dst, j.src, j.len);
+            lk.lock();
+            pending[i] = 0;
+            cv_done.notify_all();
+        }
+    }
+    void copy(uint8_t* dst, const uint8_t* src, size_t len) {
+        if (!started) start();
+        if (nhelpers == 0 || len < ((size_t)1 << 20) || !user_mu.try_lock()) { memcpy(dst, src, len); return; }
+        const int parts = nhelpers + 1;
+        const size_t per = ((len / parts) + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (int i = 0; i < nhelpers; i++) {
+                size_t off = per * (i + 1);
+                size_t l = off >= len ? 0 : (i == nhelpers - 1 ? len - off : (off + per > len ? len - off : per));
+                jobs[i] = {dst + off, src + off, l};
+                pending[i] = 1;
+            }
+            cv_work.notify_all();
+        }
+        memcpy(dst, src, per < len ? per : len);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { for (int i = 0; i < nhelpers; i++) if (pending[i]) return false; return true; });
+        }
+        user_mu.unlock();
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; cv_work.notify_all(); }
+        for (int i = 0; i < nhelpers; i++) if (th[i].joinable()) th[i].join();
+    }
+};
+CopyPool g_copy_pool;
+}  // namespace
+
 // Asynchronous on `st` when the source is page-locked; from pageable memory the bytes go through the ctx's pinned
 // ring (the calling thread copies chunk i+1 while chunk i is in flight), so `src` may be reused as soon as this returns.
 static int h2d(zk_ctx* ctx, void* dst, const uint8_t* src, size_t bytes, cudaStream_t st) {
@@ -994,7 +1093,7 @@ static int h2d(zk_ctx* ctx, void* dst, const uint8_t* src, size_t bytes, cudaStr
             CK(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[slot], cudaEventDisableTiming));
         }
         if (ctx->stage_busy[slot]) CK(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));
-        memcpy(ctx->stage[slot], src + off, len);
+        g_copy_pool.copy(ctx->stage[slot], src + off, len);
         CK(ctx, cudaMemcpyAsync((uint8_t*)dst + off, ctx->stage[slot], len, cudaMemcpyHostToDevice, st));
         CK(ctx, cudaEventRecord(ctx->stage_ev[slot], st));
         ctx->stage_busy[slot] = true;
@@ -1312,8 +1411,9 @@ static int msm_plan(zk_ctx* ctx, size_t n, size_t nmsm, const Precomp* pc, MsmPl
 
 // scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
 // Batch mode (nmsm > 1): seg_dev = nmsm+1 offsets in HBM; out_ext_dev receives nmsm extended points.
+// fused_out32 != nullptr (single MSM only): the tail also encodes, into that device buffer (k_combine_encode).
 static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split,
-                       void* out_ext_dev, const uint32_t* seg_dev = nullptr, bool shared_points = false) {
+                       void* out_ext_dev, const uint32_t* seg_dev = nullptr, bool shared_points = false, void* fused_out32 = nullptr) {
     cudaStream_t st = ctx->stream;
     const size_t n = p.n, nmsm = p.nmsm;
     if (n == 0) {
@@ -1323,6 +1423,10 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
         }
         k_set_identity_batch<<<grid_for(nmsm, 128), 128, 0, st>>>((uint4*)out_ext_dev, nmsm);
         LAUNCH_CHECK(ctx);
+        if (fused_out32) {
+            k_ext_sum_encode<<<1, 32, 0, st>>>((const uint4*)out_ext_dev, 1, (uint4*)fused_out32);
+            LAUNCH_CHECK(ctx);
+        }
         return ZK_OK;
     }
     const int W1 = p.W1, c = p.c, WB = p.WB;
@@ -1378,15 +1482,22 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
     }
-    k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev);
+    if (fused_out32 && nmsm == 1)
+        k_combine_encode<<<1, 32, 0, st>>>(w_in, WB, W1, (uint4*)out_ext_dev, (uint4*)fused_out32);
+    else
+        k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev);
     LAUNCH_CHECK(ctx);
     return ZK_OK;
 }
 
+// Read the 32-byte encoding in ctx->out32 back (after encoding the sum of g partials first, unless the pipeline's fused
+// tail already did: ext_dev == nullptr).
 static int finish_encode(zk_ctx* ctx, const void* ext_dev, size_t g, uint8_t out32[32]) {
     TRY(ensure(ctx, ctx->out32, 32));
-    k_ext_sum_encode<<<1, 32, 0, ctx->stream>>>((const uint4*)ext_dev, g, (uint4*)ctx->out32.p);
-    LAUNCH_CHECK(ctx);
+    if (ext_dev) {
+        k_ext_sum_encode<<<1, 32, 0, ctx->stream>>>((const uint4*)ext_dev, g, (uint4*)ctx->out32.p);
+        LAUNCH_CHECK(ctx);
+    }
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1448,7 +1559,7 @@ static int start_upload_decode(zk_ctx* ctx, const uint8_t* points32_host, size_t
 // Everything of a mixed (static table prefix + dynamic compressed suffix) MSM up to the extended result in
 // ctx->out_ext and the reject index in ctx->h_out[32..40): queued, not waited for.
 static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
-                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn) {
+                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, bool fuse_encode) {
     const size_t n = n_static + n_dyn;
     Precomp pc;
     const bool use_pc = n_dyn == 0 && n_static && table_precomp(t, offset, n_static, &pc);
@@ -1456,6 +1567,7 @@ static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int np
     TRY(msm_plan(ctx, n, 1, use_pc ? &pc : nullptr, &plan));
     TRY(ensure(ctx, ctx->scalars, n * 32));
     TRY(ensure(ctx, ctx->out_ext, 128));
+    TRY(ensure(ctx, ctx->out32, 32));
     TRY(ensure(ctx, ctx->comp, n_dyn * 32));
     TRY(ensure(ctx, ctx->dyn_table, n_dyn * 96));
     TRY(ensure(ctx, ctx->bad, 8));
@@ -1470,14 +1582,15 @@ static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int np
     }
     TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
-    TRY(msm_enqueue(ctx, plan, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, ctx->out_ext.p));
+    TRY(msm_enqueue(ctx, plan, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, ctx->out_ext.p, nullptr, false,
+                    fuse_encode ? ctx->out32.p : nullptr));
     if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], st));
     CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));    // after the join inside the pipeline
     return ZK_OK;
 }
 
-int zk_internal_enqueue_partial(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
-                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn) {
+static int enqueue_partial_checked(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
+                                   const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn, bool fuse_encode) {
     if (!ctx) return ZK_ERR_ARG;
     size_t sb = 0;
     for (int k = 0; k < npieces; k++) { if (pieces[k].bytes && !pieces[k].host) return ZK_ERR_ARG; sb += pieces[k].bytes; }
@@ -1485,9 +1598,13 @@ int zk_internal_enqueue_partial(zk_ctx* ctx, const zk_host_piece* pieces, int np
     if (n_static && (!t || offset > t->len || n_static > t->len - offset)) return ZK_ERR_ARG;
     if (n_dyn && (!scalars_dyn32_host || !points_dyn32_host)) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
-    int rc = enqueue_partial_impl(ctx, pieces, npieces, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn);
+    int rc = enqueue_partial_impl(ctx, pieces, npieces, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn, fuse_encode);
     if (rc != ZK_OK) quiesce(ctx);
     return rc;
+}
+int zk_internal_enqueue_partial(zk_ctx* ctx, const zk_host_piece* pieces, int npieces, const zk_table* t, size_t offset, size_t n_static,
+                                const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host, size_t n_dyn) {
+    return enqueue_partial_checked(ctx, pieces, npieces, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn, false);
 }
 void* zk_internal_partial_ptr(zk_ctx* ctx) { return ctx->out_ext.p; }
 int zk_internal_finish_partial(zk_ctx* ctx, size_t* bad_index) {
@@ -1503,8 +1620,8 @@ extern "C" int zk_msm_vartime_mixed(zk_ctx* ctx, const uint8_t* scalars_static32
     if (!ctx || !out32) return ZK_ERR_ARG;
     if (n_static && !scalars_static32_host) return ZK_ERR_ARG;
     zk_host_piece piece = {scalars_static32_host, n_static * 32};
-    TRY(zk_internal_enqueue_partial(ctx, &piece, 1, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn));
-    int rc = finish_encode(ctx, ctx->out_ext.p, 1, out32);
+    TRY(enqueue_partial_checked(ctx, &piece, 1, t, offset, n_static, scalars_dyn32_host, points_dyn32_host, n_dyn, true));
+    int rc = finish_encode(ctx, nullptr, 1, out32);
     if (rc != ZK_OK) { quiesce(ctx); return rc; }
     unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
     if (n_dyn && b != ~0ull) { memset(out32, 0, 32); return ZK_ERR_INVALID_POINT; }
