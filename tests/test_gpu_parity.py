@@ -122,6 +122,27 @@ def test_msm_adversarial_inputs(ctx, c_oracle):
     assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, b"", b"")) == bytes(32)     # empty MSM = identity
 
 
+def test_skewed_digit_distributions(ctx, c_oracle):
+    """Scalars that pile entries into few buckets (one window's digit identical for every term, half the terms equal,
+    all equal) at sizes where a bucket is split into many tasks: the counting sort and the task planner are exact for any
+    distribution."""
+    import zkvm_b200 as zk
+    for n in (33, 3000, 70000):
+        pts = make_points(c_oracle, n, 600 + n)
+        tab = zk.PointTable(ctx).append_compressed(pts)
+        skew = rand_scalars(n, 601 + n).copy(); skew[:, 7] = 0x5a; skew[:, 8] = 0xc3          # bits 56..71 equal for all
+        half = rand_scalars(n, 602 + n).copy(); half[: n // 2] = half[0]                       # half the terms identical
+        for name, sc in {"one_hot_window": skew, "half_equal": half, "all_equal": np.tile(rand_scalars(1, 9), (n, 1))}.items():
+            want = c_oracle.msm(sc, pts, n, threads=4)
+            for c in (0, 6, 11):
+                ctx.set_window(c)
+                try:
+                    assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want, (n, name, c)
+                finally:
+                    ctx.set_window(0)
+            assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want, (n, name)
+
+
 def test_invalid_point_anywhere_rejects(ctx, c_oracle, rfc_vectors):
     import zkvm_b200 as zk
     n = 2048

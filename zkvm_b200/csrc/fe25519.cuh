@@ -294,18 +294,32 @@ ZK_HD ZK_INLINE bool fe_sqrt_ratio_post(fe& r, const sqrt_ratio_state& st, const
     fe_abs(r, t);
     return correct | flipped;
 }
+// SQRT_RATIO_M1(1, v), the form both Decode and Encode use: the general routine's three multiplications by u = 1 (and
+// by the constant -i) are skipped.  Same outputs as fe_sqrt_ratio_m1(r, 1, v), bit for bit.
+template <class Ops = fe_ops_inline>
+ZK_HD inline bool fe_invsqrt(fe& r, const fe& v) {
+    fe v3, v7, p, t, check, ri;
+    Ops::sqr(v3, v); Ops::mul(v3, v3, v);                   // v^3
+    Ops::sqr(v7, v3); Ops::mul(v7, v7, v);                  // v^7
+    fe_pow22523_ops<Ops>(p, v7);
+    Ops::mul(t, p, v3);                                     // v^3 (v^7)^((p-5)/8)
+    Ops::sqr(check, t); Ops::mul(check, check, v);          // v r^2
+    const fe one = fe_one(), i = fe_sqrt_m1();
+    fe m1, mi;
+    fe_neg(m1, one); fe_neg(mi, i);
+    bool correct = fe_eq(check, one);
+    bool flipped = fe_eq(check, m1);
+    bool flipped_i = fe_eq(check, mi);
+    Ops::mul(ri, t, i);
+    fe_select(t, t, ri, flipped | flipped_i);
+    fe_abs(r, t);
+    return correct | flipped;
+}
 ZK_HD inline bool fe_sqrt_ratio_m1(fe& r, const fe& u, const fe& v) {
     sqrt_ratio_state st; fe p;
     fe_sqrt_ratio_pre(st, u, v);
     fe_pow22523(p, st.t);
     return fe_sqrt_ratio_post(r, st, p, u, v);
-}
-template <class Ops>
-ZK_HD inline bool fe_sqrt_ratio_m1_ops(fe& r, const fe& u, const fe& v) {
-    sqrt_ratio_state st; fe p;
-    fe_sqrt_ratio_pre<Ops>(st, u, v);
-    fe_pow22523_ops<Ops>(p, st.t);
-    return fe_sqrt_ratio_post<Ops>(r, st, p, u, v);
 }
 
 }  // namespace zk

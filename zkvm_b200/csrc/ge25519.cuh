@@ -121,9 +121,9 @@ ZK_HD ZK_INLINE bool ristretto_decode_post(fe& x, fe& y, fe& t, const decode_sta
 }
 // Returns false on any reject rule.
 ZK_HD inline bool ristretto_decode(fe& x, fe& y, fe& t, const uint32_t w[8]) {
-    decode_state d; fe isr, one = fe_one();
+    decode_state d; fe isr;
     ristretto_decode_pre(d, w);
-    bool was_square = fe_sqrt_ratio_m1(isr, one, d.arg);
+    bool was_square = fe_invsqrt(isr, d.arg);
     return ristretto_decode_post(x, y, t, d, isr, was_square);
 }
 // Two decodes sharing one interleaved exponentiation chain (see fe2).
@@ -144,11 +144,11 @@ ZK_HD inline void ristretto_decode_x2(fe& x0, fe& y0, fe& t0, bool& ok0, const u
 // throughput kernels, fe_ops_call in the single-warp tail).
 template <class Ops>
 ZK_HD inline void ristretto_encode_ops(uint32_t out[8], const ge_ext& p) {
-    fe u1, u2, t0, t1, isr, den1, den2, zinv, ix0, iy0, ench, x, y, dinv, one = fe_one();
+    fe u1, u2, t0, t1, isr, den1, den2, zinv, ix0, iy0, ench, x, y, dinv;
     fe_add(t0, p.Z, p.Y); fe_sub(t1, p.Z, p.Y); Ops::mul(u1, t0, t1);
     Ops::mul(u2, p.X, p.Y);
     Ops::sqr(t0, u2); Ops::mul(t0, t0, u1);
-    fe_sqrt_ratio_m1_ops<Ops>(isr, one, t0);
+    fe_invsqrt<Ops>(isr, t0);
     Ops::mul(den1, isr, u1);
     Ops::mul(den2, isr, u2);
     Ops::mul(zinv, den1, den2); Ops::mul(zinv, zinv, p.T);

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_from_extended(const uint4* __restrict__
     const bool z_zero = fe_is_zero(c[2]);
     const bool u_zero = fe_is_zero(u);
     fe_mul(wv, u, zz);
-    bool sq = fe_sqrt_ratio_m1(r, one, wv);                         // r^2 = 1 / (u Z^2) when that is a square
+    bool sq = fe_invsqrt(r, wv);                                    // r^2 = 1 / (u Z^2) when that is a square
     fe_sqr(zi, r); fe_mul(zi, zi, u); fe_mul(zi, zi, c[2]);         // Z * r^2 * u = 1/Z
     fe_mul(x, c[0], zi); fe_mul(y, c[1], zi);
     // y = +-1 (u == 0, so x must be 0): the square-root route degenerates; y = Y/Z is +1 or -1 by comparison
