@@ -33,7 +33,10 @@ namespace {
 
 constexpr int REDUCE_RADIX_LOG2 = 3;               // tree fan-in 8
 constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
-constexpr size_t TREE_WARP_MAX_NODES = 2048;        // upper tree levels with at most this many nodes use a warp per node
+#ifndef ZK_TREE_WARP_MAX
+#define ZK_TREE_WARP_MAX 2048
+#endif
+constexpr size_t TREE_WARP_MAX_NODES = ZK_TREE_WARP_MAX;   // upper tree levels with at most this many nodes use a warp per node
 constexpr uint32_t TASK_LEN = 64;                   // longest run of entries one accumulation thread walks
 
 // Window geometry.  A scalar (< 2^253 after reduction) is cut into W signed digits covering 254 bits; the widths are
@@ -1280,12 +1283,12 @@ extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
     const int W = windows_for_width(c);
     c = max_width(W);
     if ((unsigned long long)len * W >= (1ull << 31)) return ZK_ERR_ARG;
-    uint4* pre = nullptr; uint4* scratch = nullptr;
+    uint4* pre = nullptr;
+    TRY(ensure(ctx, ctx->inv_scratch, len * (size_t)(W - 1) * 128));      // the doubling chains' extended points, kept in the workspace
+    uint4* scratch = (uint4*)ctx->inv_scratch.p;
     CK(ctx, cudaMalloc((void**)&pre, len * W * 96));
-    cudaError_t e = cudaMalloc((void**)&scratch, len * (size_t)(W - 1) * 128);
-    if (e != cudaSuccess) { cudaFree(pre); CK(ctx, e); }
     cudaStream_t st = ctx->stream;
-    e = cudaMemcpyAsync(pre, t->d, len * 96, cudaMemcpyDeviceToDevice, st);             // window 0 = the points themselves
+    cudaError_t e = cudaMemcpyAsync(pre, t->d, len * 96, cudaMemcpyDeviceToDevice, st);             // window 0 = the points themselves
     if (e == cudaSuccess) {
         const size_t m = len * (size_t)(W - 1);
         k_precomp_double<<<grid_for(len, 128), 128, 0, st>>>(t->d, len, W, scratch);
@@ -1294,7 +1297,6 @@ extern "C" int zk_table_precompute(zk_ctx* ctx, zk_table* t, int c) {
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(scratch);
     if (e != cudaSuccess) { cudaFree(pre); CK(ctx, e); }
     t->pre = pre; t->pre_len = len; t->pre_c = c; t->pre_W = W;
     return ZK_OK;
