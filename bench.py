@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="points per GPU (default 2^20, the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip sweep / strong / batch / shapes (headline numbers only)")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="MSMs in flight: each uses its own context (stream + workspace), so the serial tail of one step "
                          "(Horner + encode, a few warps) overlaps the next step's accumulation; 1 = strictly serial")
     return ap.parse_args()
@@ -295,16 +295,18 @@ def run_cuda(a):
     for s in range(SETS): gate(f"table_set{s}", r[s] if rank == 0 else None, want[s])
 
     # the host-buffer path (per process) with the combine actually finished on rank 0
-    ones = np.frombuffer((1).to_bytes(32, "little") * world, dtype=np.uint8)
-    comb_ctx = zk.Context(local) if (world > 1 and rank == 0) else None
+    comb_ctx = None
+    if world > 1 and rank == 0:
+        comb_ctx = zk.Context(local); comb_ctx.set_priority(True)     # its one small kernel must not queue behind bulk work
 
     def finish_gather(enc):
-        """N > 1: gather the N 32-byte partial encodings on the host; rank 0 adds them on its GPU (decode + add + encode)."""
+        """N > 1: gather the N 32-byte partial encodings on the host; rank 0 adds them on its GPU (zk_sum_compressed:
+        decode + add + encode in one small launch)."""
         if world == 1: return enc
         lst = [torch.zeros(32, dtype=torch.uint8) for _ in range(world)]
         dist.all_gather(lst, torch.frombuffer(bytearray(bytes(enc)), dtype=torch.uint8), group=host_pg)
         if rank != 0: return None
-        return zk.RistrettoPoint.optional_multiscalar_mul(comb_ctx, ones, np.concatenate([t.numpy() for t in lst]))
+        return comb_ctx.sum_compressed(np.concatenate([t.numpy() for t in lst]))
 
     for s in range(SETS):
         gate(f"host_compressed_set{s}", finish_gather(zk.RistrettoPoint.optional_multiscalar_mul(ctx, np_scal[s], np_comp[s])), want[s])

@@ -59,6 +59,9 @@ void zk_ctx_destroy(zk_ctx* ctx);
 int zk_ctx_sync(zk_ctx* ctx);
 /* cudaStream_t of the ctx as an opaque pointer (for CUDA-event timing by the caller). */
 void* zk_ctx_stream(zk_ctx* ctx);
+/* high = 1: recreate the ctx's streams with the device's highest stream priority, so that its (small) kernels are
+ * scheduled ahead of other contexts' bulk work; 0 restores the default.  Call while the ctx is idle. */
+int zk_ctx_set_priority(zk_ctx* ctx, int high);
 
 /* ---- host buffers ----
  * Every `*_host` pointer may be ordinary PAGEABLE memory (a Rust Vec<u8>).  Uploads of 256 KiB or more from pageable
@@ -162,6 +165,10 @@ int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk_table* t, 
                      void* out_ext128_dev);
 /* Sum g extended points (g*128 bytes in HBM, e.g. the all-gathered partials) and encode. */
 int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]);
+/* out32 = Encode(sum_i Decode(points[i])), g <= 1024, in ONE small kernel launch: the combine step of a deployment
+ * with one process per GPU, where every process returns the 32-byte encoding of its partial MSM
+ * (the sum of RistrettoPoints, `iter.sum()`).  ZK_ERR_INVALID_POINT if an encoding is rejected. */
+int zk_sum_compressed(zk_ctx* ctx, const uint8_t* points32_host, size_t g, uint8_t out32[32]);
 /* Is the ristretto255 element the identity?  (the accept test of both verifiers) */
 int zk_encoding_is_identity(const uint8_t enc32[32]);
 

@@ -143,6 +143,24 @@ def test_skewed_digit_distributions(ctx, c_oracle):
             assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want, (n, name)
 
 
+def test_sum_compressed(ctx, c_oracle, rfc_vectors):
+    """zk_sum_compressed: the combine step of a one-process-per-GPU deployment, against the oracle's point sum."""
+    import zkvm_b200 as zk
+    pts = make_points(c_oracle, 1024, 4242)
+    for g in (0, 1, 2, 7, 255, 256, 257, 300, 1024):
+        got = ctx.sum_compressed(pts[:32 * g])
+        want = c_oracle.point_sum(pts[:32 * g], g) if g else bytes(32)
+        assert got is not None and bytes(got) == want, g
+    bad = bytearray(pts[:32 * 300]); bad[32 * 299:32 * 300] = H(rfc_vectors["bad_encodings"]["negative_s"][0])
+    assert ctx.sum_compressed(bytes(bad)) is None
+    with pytest.raises(zk.ZkError):
+        ctx.sum_compressed(pts + pts[:32])            # more than 1024 points
+    hp = zk.Context(0); hp.set_priority(True)         # a high-priority context computes the same bytes
+    assert bytes(hp.sum_compressed(pts[:32 * 9])) == c_oracle.point_sum(pts[:32 * 9], 9)
+    assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(hp, rand_scalars(100, 1), pts[:3200])) == c_oracle.msm(rand_scalars(100, 1), pts[:3200], 100)
+    hp.close()
+
+
 def test_invalid_point_anywhere_rejects(ctx, c_oracle, rfc_vectors):
     import zkvm_b200 as zk
     n = 2048

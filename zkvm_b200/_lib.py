@@ -48,6 +48,8 @@ SYMBOLS = [
     ("zk_msm_vartime_table_batch", _i, [_vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("zk_msm_table_dev", _i, [_vp, _vp, _vp, _sz, _sz, _vp]),
     ("zk_ext_sum_compress_dev", _i, [_vp, _vp, _sz, _vp]),
+    ("zk_sum_compressed", _i, [_vp, _vp, _sz, _vp]),
+    ("zk_ctx_set_priority", _i, [_vp, _i]),
     ("zk_encoding_is_identity", _i, [_vp]),
     ("zk_ctx_set_window", _i, [_vp, _i]),
     ("zk_pick_window", _i, [_sz]),

@@ -146,6 +146,14 @@ struct RistrettoPoint {
         return out;
     }
     static bool is_identity(const CompressedRistretto& c) { return zk_encoding_is_identity(c.data()) != 0; }
+    // sum of decompressed points, compressed (at most 1024); nullopt if an encoding is invalid
+    static std::optional<CompressedRistretto> sum(Context& ctx, const std::vector<CompressedRistretto>& points) {
+        CompressedRistretto out{};
+        int rc = zk_sum_compressed(ctx.raw(), reinterpret_cast<const uint8_t*>(points.data()), points.size(), out.data());
+        if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
+        ctx.check(rc);
+        return out;
+    }
 };
 
 // Several GPUs of one box behind one call (BASELINE.json config 5): point-range shards, one gather of 128-byte partials.

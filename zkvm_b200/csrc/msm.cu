@@ -798,6 +798,40 @@ __global__ void k_ext_sum_encode(const uint4* __restrict__ ext, size_t g, uint4*
     out32[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// out32 = Encode(sum_i Decode(in[i])), g <= 1024 encodings, ONE launch of one CTA: thread i decodes point i (and folds
+// points i + 256, ... into it), a shared-memory tree adds the per-thread sums, thread 0 encodes.  *bad = lowest rejected
+// index.  This is the combine step of a multi-process deployment (every process returns the encoding of its partial MSM).
+__global__ void __launch_bounds__(256) k_sum_compressed(const uint4* __restrict__ in, uint32_t g, uint4* __restrict__ out32,
+                                                        unsigned long long* __restrict__ bad) {
+    __shared__ uint4 sh[256 * 8];
+    const uint32_t t = threadIdx.x;
+    ge_ext acc; ge_identity(acc);
+    for (uint32_t i = t; i < g; i += 256) {
+        uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        fe x, y, tt;
+        if (ristretto_decode(x, y, tt, w)) {
+            ge_niels q; ge_to_niels_affine(q, x, y, tt);
+            ge_madd(acc, acc, q, false);
+        } else atomicMin(bad, (unsigned long long)i);
+    }
+    st_ext(sh, t, acc);
+    __syncthreads();
+    for (uint32_t stride = 128; stride >= 1; stride >>= 1) {
+        if (t < stride && t + stride < 256 && t + stride < g) {
+            ge_ext p, q; ld_ext(p, sh, t); ld_ext(q, sh, t + stride);
+            ge_add(p, p, q); st_ext(sh, t, p);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        ge_ext p; ld_ext(p, sh, 0);
+        uint32_t o[8]; ristretto_encode_ops<fe_ops_call>(o, p);
+        out32[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        out32[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 // Single-MSM tail in ONE launch: Horner over the window sums (one quad), then RFC 9496 Encode (one thread) -- the
 // extended result is also left in out_ext for callers that want it.  Saves a kernel boundary on the serial tail.
 __global__ void __launch_bounds__(32) k_combine_encode(const uint4* __restrict__ wt, int windows, int geomW,
@@ -1724,6 +1758,44 @@ extern "C" int zk_msm_vartime_table_batch(zk_ctx* ctx, const uint8_t* scalars32_
                                           const uint64_t* seg_offsets, size_t m, uint8_t* out32s) {
     if (!t) return ZK_ERR_ARG;
     return batch_common(ctx, scalars32_host, nullptr, t, offset, seg_offsets, m, out32s, nullptr);
+}
+
+extern "C" int zk_sum_compressed(zk_ctx* ctx, const uint8_t* points32_host, size_t g, uint8_t out32[32]) {
+    if (!ctx || !out32 || (g && !points32_host) || g > 1024) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->comp, g * 32 + 32));
+    TRY(ensure(ctx, ctx->out32, 32));
+    TRY(ensure(ctx, ctx->bad, 8));
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
+    if (g) CK(ctx, cudaMemcpyAsync(ctx->comp.p, points32_host, g * 32, cudaMemcpyHostToDevice, st));
+    k_sum_compressed<<<1, 256, 0, st>>>((const uint4*)ctx->comp.p, (uint32_t)g, (uint4*)ctx->out32.p, (unsigned long long*)ctx->bad.p);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 32, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
+    if (b != ~0ull) { memset(out32, 0, 32); return ZK_ERR_INVALID_POINT; }
+    memcpy(out32, ctx->h_out, 32);
+    return ZK_OK;
+}
+
+// Recreate the ctx's streams with the device's highest (1) or default (0) priority.  Call before queueing work.
+extern "C" int zk_ctx_set_priority(zk_ctx* ctx, int high) {
+    if (!ctx) return ZK_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int lo = 0, hi = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int prio = high ? hi : 0;
+    cudaStream_t* all[3] = {&ctx->stream, &ctx->aux[0], &ctx->aux[1]};
+    for (cudaStream_t* sp : all) {
+        CK(ctx, cudaStreamSynchronize(*sp));
+        cudaStream_t ns = nullptr;
+        CK(ctx, cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, prio));
+        CK(ctx, cudaStreamDestroy(*sp));
+        *sp = ns;
+    }
+    return ZK_OK;
 }
 
 extern "C" int zk_encoding_is_identity(const uint8_t enc32[32]) {

@@ -165,6 +165,21 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.zk_ctx_launch_count(self._h))
 
+    def set_priority(self, high: bool):
+        """Recreate the context's streams with the highest (or default) stream priority; call while idle."""
+        self._check(self._lib.zk_ctx_set_priority(self._h, 1 if high else 0))
+
+    def sum_compressed(self, points) -> Optional["CompressedRistretto"]:
+        """Sum of up to 1024 compressed points in one small launch (`iter.sum()` over decompressed points, compressed);
+        None if an encoding is invalid."""
+        h, g = _join32(points)
+        out = C.create_string_buffer(32)
+        rc = self._lib.zk_sum_compressed(self._h, _ptr(h), g, out)
+        if rc == _lib.ZK_ERR_INVALID_POINT:
+            return None
+        self._check(rc)
+        return CompressedRistretto(out.raw)
+
     def set_staging(self, mode: int):
         """0 = auto (pinned ring for pageable sources), 1 = never stage, 2 = always stage."""
         self._check(self._lib.zk_ctx_set_staging(self._h, mode))
@@ -467,6 +482,21 @@ class MultiGpu:
 
     def set_gather(self, mode: str):
         self._check(self._lib.zk_mgpu_set_gather(self._h, {"peer": 0, "nccl": 1}[mode]))
+
+    def set_priority(self, high: bool):
+        """Recreate the context's streams with the highest (or default) stream priority; call while idle."""
+        self._check(self._lib.zk_ctx_set_priority(self._h, 1 if high else 0))
+
+    def sum_compressed(self, points) -> Optional["CompressedRistretto"]:
+        """Sum of up to 1024 compressed points in one small launch (`iter.sum()` over decompressed points, compressed);
+        None if an encoding is invalid."""
+        h, g = _join32(points)
+        out = C.create_string_buffer(32)
+        rc = self._lib.zk_sum_compressed(self._h, _ptr(h), g, out)
+        if rc == _lib.ZK_ERR_INVALID_POINT:
+            return None
+        self._check(rc)
+        return CompressedRistretto(out.raw)
 
     def set_staging(self, mode: int):
         self._check(self._lib.zk_mgpu_set_staging(self._h, mode))
