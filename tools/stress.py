@@ -13,6 +13,8 @@ L = zk.GROUP_ORDER
 pool_n = 1 << 17
 pool = c_oracle.from_uniform(rng.integers(0, 256, size=(pool_n, 64), dtype=np.uint8), pool_n)
 plain = zk.PointTable(ctx).append_compressed(pool)
+import torch
+mg = zk.MultiGpu(g=min(torch.cuda.device_count(), 8))
 t_end = time.time() + seconds
 it = 0
 def scalars(n):
@@ -39,6 +41,16 @@ while time.time() < t_end:
     k = int(rng.integers(0, n + 1))
     assert bytes(zk.RistrettoPoint.mixed_multiscalar_mul(ctx, sc[:k], plain, sc[k:], pts[32 * k:], offset=off)) == want, ("mixed", it, n, k)
     ctx.set_window(0)
+    if it % 3 == 0:                                   # single-process multi-GPU entry point, pageable and staged sources
+        mg.set_staging(2 if it % 6 == 0 else 0)
+        assert bytes(mg.optional_multiscalar_mul(sc, pts)) == want, ("mgpu", it, n)
+    if it % 4 == 0:
+        ctx.set_staging(2)
+        assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want, ("staged", it, n)
+        ctx.set_staging(0)
+    if it % 8 == 0:
+        g = min(n, int(rng.integers(1, 1025)))
+        assert bytes(ctx.sum_compressed(pts[:32 * g])) == c_oracle.point_sum(pts[:32 * g], g), ("sum", it, g)
     if it % 7 == 0:
         pre = zk.PointTable(ctx).append_compressed(pts).precompute(int(rng.integers(4, 21)))
         assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, pre)) == want, ("precomputed", it, n)
