@@ -603,21 +603,44 @@ __device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const
     fe val; fe_select(val, dif, sum, (q & 1) != 0);             // lane1: B+A = H, lane3: D+C = G
     quad_finish(r, val, c);
 }
-// r = 2p.
-__device__ __forceinline__ void quad_dbl(fe& r, const fe& p, const quad_ctx& c) {
+// r = 2p, for chains of doublings (window Horner, the tree's weight shifts).  Compared with the straightforward lane
+// assignment (every lane squares its own coordinate, lane 3 squares X+Y, t/A/B broadcast, two fetches before the final
+// product: 56 shuffles) this takes 32 shuffles and one exchange round fewer:
+// The lane that squares (X+Y) is the one that then owns E, so it needs no broadcast of t; every lane owns one factor of
+// its final product and fetches the other with ONE shuffle (E <- F, F <- G, G <- H, H <- E).  The price is that the
+// products land permuted: X and Z stay in lanes 0 and 2, Y and T swap lanes 1 and 3 on every doubling.  SW = the layout
+// on entry (false: X Y Z T, true: X T Z Y); the result has layout !SW.  T is not an input of a doubling.
+// Single-warp latency (tools/ubench/quad_latency.cu): 1386 cycles against 1510 for the straightforward form; exchanging
+// through shared memory instead of shuffles was measured too and is slower (1540).
+template <bool SW>
+__device__ __forceinline__ void quad_dbl_chain(fe& r, const fe& p, const quad_ctx& c) {
     const int q = c.q;
-    fe x0, y0, s, opnd, sq, A, Bv, t, apb, bma, c2, L, R, val, z = fe_zero();
-    fe_shfl(x0, p, c.base, c.mask); fe_shfl(y0, p, c.base + 1, c.mask);
-    fe_add(s, x0, y0);
-    fe_select(opnd, p, s, q == 3);
-    fe_sqr(sq, opnd);                                           // X^2 | Y^2 | Z^2 | (X+Y)^2
-    fe_shfl(A, sq, c.base, c.mask); fe_shfl(Bv, sq, c.base + 1, c.mask); fe_shfl(t, sq, c.base + 3, c.mask);
+    const int lx = c.base, lz = c.base + 2, ly = c.base + (SW ? 3 : 1), lt = c.base + (SW ? 1 : 3);
+    const bool isx = q == 0, isz = q == 2, isy = q == (SW ? 3 : 1), ist = q == (SW ? 1 : 3);
+    fe got, s, opnd, sq, A, Bv, apb, bma, c2, L, R, val, oth, z = fe_zero();
+    fe_shfl(got, p, isx ? ly : (ist ? lx : c.base + q), c.mask);     // X-holder gets Y, T-holder gets X
+    fe_add(s, p, got);
+    fe_select(opnd, p, s, isx); fe_select(opnd, opnd, got, ist);     // X+Y | Y | Z | X
+    fe_sqr(sq, opnd);                                               // t | B | Z^2 | A
+    fe_shfl(A, sq, lt, c.mask); fe_shfl(Bv, sq, ly, c.mask);
     fe_add(apb, A, Bv); fe_sub(bma, Bv, A); fe_add(c2, sq, sq);
-    fe_select(L, bma, t, q == 0); fe_select(L, L, z, q == 1);    // t | 0 | B-A | B-A
-    fe_select(R, apb, c2, q == 2); fe_select(R, R, z, q == 3);   // A+B | A+B | 2Z^2 | 0
-    fe_sub(val, L, R);                                          // E | H | F | G
-    quad_finish(r, val, c);
+    fe_select(L, bma, sq, isx); fe_select(L, L, z, isy);             // t | 0 | B-A | B-A
+    fe_select(R, apb, c2, isz); fe_select(R, R, z, ist);             // A+B | A+B | 2Z^2 | 0
+    fe_sub(val, L, R);                                              // E | H | F | G   (holders of X | Y | Z | T)
+    fe_shfl(oth, val, isx ? lz : (isz ? lt : (ist ? ly : lx)), c.mask);   // E<-F, F<-G, G<-H, H<-E
+    fe_mul(r, val, oth);                                            // X3 = EF | T3 = EH | Z3 = FG | Y3 = GH
 }
+// k doublings of the quad's point, standard layout in and out.
+__device__ __forceinline__ void quad_dbl_n(fe& acc, int k, const quad_ctx& c) {
+#pragma unroll 1
+    for (; k >= 2; k -= 2) { quad_dbl_chain<false>(acc, acc, c); quad_dbl_chain<true>(acc, acc, c); }
+    if (k == 1) {
+        quad_dbl_chain<false>(acc, acc, c);
+        fe sw; fe_shfl(sw, acc, c.base + (c.q == 1 ? 3 : (c.q == 3 ? 1 : c.q)), c.mask);      // Y and T back to lanes 1 and 3
+        acc = sw;
+    }
+}
+
 __device__ __forceinline__ void quad_neg(fe& r, const fe& p, int q) { fe_cneg(r, p, q == 0 || q == 3); }
 __device__ __forceinline__ void quad_ld(fe& r, const uint4* base, size_t idx, int q) { ld_fe_plain(r, base + idx * 8 + q * 2); }
 __device__ __forceinline__ void quad_st(uint4* base, size_t idx, int q, const fe& r) { st_fe(base + idx * 8 + q * 2, r); }
@@ -702,8 +725,7 @@ __global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(cons
             quad_add(wsum, wsum, tmp, c);
         }
         quad_neg(tmp, run, q); quad_add(acc, acc, tmp, c);      // sum i*A_i
-#pragma unroll 1
-        for (int d = 0; d < log2_wc; d++) quad_dbl(acc, acc, c);
+        quad_dbl_n(acc, log2_wc, c);
         quad_add(acc, acc, wsum, c);
     }
     if (active) { quad_st(a_out, t, q, run); quad_st(wt_out, t, q, acc); }
@@ -744,8 +766,7 @@ __global__ void __launch_bounds__(128) k_tree_level_warp(const uint4* __restrict
     }
     fe run; fe_shfl(run, S, q, 0xffffffffu);               // S_0 = plain sum, from quad 0
     quad_neg(tmp, run, q); quad_add(R, R, tmp, c);         // sum_i i*A_i
-#pragma unroll 1
-    for (int d = 0; d < log2_wc; d++) quad_dbl(R, R, c);
+    quad_dbl_n(R, log2_wc, c);
     quad_add(R, R, Ws, c);
     if (active && quad == 0) { quad_st(a_out, node, q, run); quad_st(wt_out, node, q, R); }
 }
@@ -762,8 +783,7 @@ __global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__
     quad_ld(acc, base, windows - 1, c.q);
 #pragma unroll 1
     for (int w = windows - 2; w >= 0; w--) {
-#pragma unroll 1
-        for (int d = window_geom(geomW, w).width; d > 0; d--) quad_dbl(acc, acc, c);
+        quad_dbl_n(acc, window_geom(geomW, w).width, c);
         quad_ld(tmp, base, w, c.q);
         quad_add(acc, acc, tmp, c);
     }
@@ -843,8 +863,7 @@ __global__ void __launch_bounds__(32) k_combine_encode(const uint4* __restrict__
         quad_ld(acc, wt, windows - 1, c.q);
 #pragma unroll 1
         for (int w = windows - 2; w >= 0; w--) {
-#pragma unroll 1
-            for (int d = window_geom(geomW, w).width; d > 0; d--) quad_dbl(acc, acc, c);
+            quad_dbl_n(acc, window_geom(geomW, w).width, c);
             quad_ld(tmp, wt, w, c.q);
             quad_add(acc, acc, tmp, c);
         }
