@@ -418,9 +418,9 @@ def run_cuda(a):
 
     # one process, all N GPUs, one call (zk_mgpu_msm_vartime): what a single-process caller gets
     e2e_single = None
-    try:
-        if world > 1:
-            host_barrier()
+    if world > 1:
+        host_barrier()
+        try:
             if rank == 0:
                 # the whole job's host bytes in ONE buffer on rank 0 (rank r's shard = rank r's seeded inputs)
                 big_s = torch.empty(n * world * 32, dtype=torch.uint8).pin_memory(); big_p = torch.empty(n * world * 32, dtype=torch.uint8).pin_memory()
@@ -447,19 +447,24 @@ def run_cuda(a):
                 e2e_single = {"value": n * world * ks / dt, "unit": UNIT, "ms_per_step": dt / ks * 1e3, "steps": ks,
                               "single_call_latency_ms": lat, "host_threads": F, "gather": "peer copies (cudaMemcpyPeerAsync, 128 B per device)",
                               "api": f"zk_mgpu_msm_vartime(mg, scalars_host, points_host, {n * world}, out32): ONE process, {world} GPUs, pinned host buffers"}
+                # gather by one ncclAllGather instead of peer copies: ONE handle, calls strictly one after the other
+                # (collectives of several communicators over the same GPUs must not be issued concurrently)
                 try:
-                    for m in mgs: m.set_gather("nccl")
+                    t1 = time.perf_counter()
+                    for i in range(4): call_mg(0, i)
+                    peer_serial = (time.perf_counter() - t1) / 4 * 1e3
+                    mgs[0].set_gather("nccl")
                     gate("single_process_mgpu_nccl", call_mg(0, 0), want[0])
-                    dt2, _ = time_e2e(call_mg, ks, finish=ident, sync_ranks=False)
-                    e2e_single["nccl_gather_ms_per_step"] = dt2 / ks * 1e3
+                    t1 = time.perf_counter()
+                    for i in range(4): call_mg(0, i)
+                    e2e_single["gather_serial_call_ms"] = {"peer_copies": peer_serial, "nccl_allgather": (time.perf_counter() - t1) / 4 * 1e3}
                 except zk.ZkError as e:
                     e2e_single["nccl_gather"] = f"unavailable: {e}"
                 for m in mgs: m.close()
                 del big_s, big_p
-            host_barrier()
-    except Exception as e:                      # an extra, never a reason to lose the headline line
-        e2e_single = {"error": repr(e)}
-        if world > 1: pass
+        except Exception as e:                  # an extra, never a reason to lose the headline line (or to hang the other ranks)
+            e2e_single = {"error": repr(e)}
+        host_barrier()
 
     extras = not a.no_extras
     # ---- BASELINE config 2: sweep n = 2^10 .. 2^20 on one GPU, GPU == CPU gated per n ----------------------------
