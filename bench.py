@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="points per GPU (default 2^20, the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip sweep / strong / batch / shapes (headline numbers only)")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="host threads of the end-to-end loop (0 = one per context in flight, fewer when cores are scarce and spinning)")
     ap.add_argument("--inflight", type=int, default=4,
                     help="MSMs in flight: each uses its own context (stream + workspace), so the serial tail of one step "
                          "(Horner + encode, a few warps) overlaps the next step's accumulation; 1 = strictly serial")
@@ -190,7 +192,12 @@ def run_cuda(a):
     c_oracle.load()
     cpu_threads = max(1, host_threads() // world)
     F = max(1, a.inflight)
-    ctxs = [zk.Context(local) for _ in range(F)]
+    # host threads of the end-to-end loop: one per context in flight, but never more than the cores this rank can have
+    # (the driver's 8-GPU box exposes 32 cores: 8 ranks x 4 callers + 8 main threads would oversubscribe it)
+    cores_per_rank = host_threads() // world
+    scarce_cores = cores_per_rank < F + 4            # few cores per GPU: the e2e loop's waiting callers must not spin
+    FE = a.e2e_threads if a.e2e_threads > 0 else F   # blocked callers cost no CPU, so scarce cores do not limit their number
+    ctxs = [zk.Context(local) for _ in range(max(F, FE))]       # `value` uses the first F, the e2e loop the first FE
     ctx = ctxs[0]
     streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
     n = 1 << a.log2n
@@ -315,9 +322,9 @@ def run_cuda(a):
     run_steps(W)
     sampler = ClockSampler(local)
     if rank == 0: sampler.start()
-    launches0 = sum(c.launch_count for c in ctxs)
+    launches0 = sum(c.launch_count for c in ctxs[:F])
     ms, outs = timed(run_steps, K)
-    launches = sum(c.launch_count for c in ctxs) - launches0
+    launches = sum(c.launch_count for c in ctxs[:F]) - launches0
     if rank == 0:
         for i, o in enumerate(outs): gate("timed_steps", o, want[i % SETS])
     # single-MSM latency (one context, strictly serial) for the record
@@ -366,15 +373,15 @@ def run_cuda(a):
 
     # ---- `e2e`: host buffers through the public API; F host threads, one context each (ctypes drops the GIL) ----
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=F)
+    pool = ThreadPoolExecutor(max_workers=FE)
 
     def e2e_loop(call, k, finish=finish_gather):
         """call(f, i) -> 32-byte encoding of step i, issued from host thread f; results are finished in step order."""
-        qs = [queue.Queue() for _ in range(F)]
-        futs = [pool.submit(lambda f=f: [qs[f].put(call(f, i)) for i in range(f, k, F)]) for f in range(F)]
+        qs = [queue.Queue() for _ in range(FE)]
+        futs = [pool.submit(lambda f=f: [qs[f].put(call(f, i)) for i in range(f, k, FE)]) for f in range(FE)]
         out = []
         for i in range(k):
-            out.append(finish(qs[i % F].get()))
+            out.append(finish(qs[i % FE].get()))
         for x in futs: x.result()
         return out
 
@@ -390,6 +397,8 @@ def run_cuda(a):
         return dt, res
 
     call_pinned = lambda f, i: zk.RistrettoPoint.optional_multiscalar_mul(ctxs[f], np_scal[i % SETS], np_comp[i % SETS])
+    if scarce_cores:
+        for cx in ctxs: cx.set_wait(1)
     e2e_s, res = time_e2e(call_pinned, K)
     if rank == 0:
         for i, o in enumerate(res): gate("e2e_timed_steps", o, want[i % SETS])
@@ -432,7 +441,9 @@ def run_cuda(a):
                 if rank == 0:
                     big_s[r_ * n * 32:(r_ + 1) * n * 32] = buf_s; big_p[r_ * n * 32:(r_ + 1) * n * 32] = buf_p
             if rank == 0:
-                mgs = [zk.MultiGpu(g=world) for _ in range(F)]
+                mgs = [zk.MultiGpu(g=world) for _ in range(FE)]
+                if scarce_cores:
+                    for m in mgs: m.set_wait(1)
                 bs, bp = big_s.numpy(), big_p.numpy()
                 call_mg = lambda f, i: mgs[f].optional_multiscalar_mul(bs, bp)
                 ks = max(6, K // 2)
@@ -445,7 +456,7 @@ def run_cuda(a):
                 for i in range(3): call_mg(0, i)
                 lat = (time.perf_counter() - t1) / 3 * 1e3
                 e2e_single = {"value": n * world * ks / dt, "unit": UNIT, "ms_per_step": dt / ks * 1e3, "steps": ks,
-                              "single_call_latency_ms": lat, "host_threads": F, "gather": "peer copies (cudaMemcpyPeerAsync, 128 B per device)",
+                              "single_call_latency_ms": lat, "host_threads": FE, "gather": "peer copies (cudaMemcpyPeerAsync, 128 B per device)",
                               "api": f"zk_mgpu_msm_vartime(mg, scalars_host, points_host, {n * world}, out32): ONE process, {world} GPUs, pinned host buffers"}
                 # gather by one ncclAllGather instead of peer copies: ONE handle, calls strictly one after the other
                 # (collectives of several communicators over the same GPUs must not be issued concurrently)
@@ -466,6 +477,7 @@ def run_cuda(a):
             e2e_single = {"error": repr(e)}
         host_barrier()
 
+    for cx in ctxs: cx.set_wait(0)
     extras = not a.no_extras
     # ---- BASELINE config 2: sweep n = 2^10 .. 2^20 on one GPU, GPU == CPU gated per n ----------------------------
     sweep = None
@@ -581,7 +593,7 @@ def run_cuda(a):
         parity["oracle_seconds"] = oracle_s
         e2e = {"value": n * world * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                "h2d_bytes_per_step": 64 * n * world, "d2h_bytes_per_step": 32 * world, "single_call_latency_ms": e2e_latency_ms,
-               "host_threads": F,
+               "host_threads": FE, "host_cores_per_rank": cores_per_rank, "wait": "blocking" if scarce_cores else "spin",
                "api": "zk_msm_vartime(ctx, scalars_host, compressed_points_host, n, out32) from pinned host memory"
                       + ("; one process per GPU, partial encodings gathered on the host, rank 0 adds them on its GPU" if world > 1 else "")}
         if e2e_pageable: e2e["pageable"] = e2e_pageable

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("zk_ctx_create", _i, [_i, C.POINTER(_vp)]),
     ("zk_ctx_destroy", None, [_vp]),
     ("zk_ctx_sync", _i, [_vp]),
+    ("zk_ctx_set_wait", _i, [_vp, _i]),
     ("zk_ctx_stream", _vp, [_vp]),
     ("zk_table_create", _i, [_vp, _sz, C.POINTER(_vp)]),
     ("zk_table_destroy", None, [_vp]),
@@ -69,6 +70,7 @@ SYMBOLS = [
     ("zk_mgpu_last_error", C.c_char_p, [_vp]),
     ("zk_mgpu_set_gather", _i, [_vp, _i]),
     ("zk_mgpu_set_staging", _i, [_vp, _i]),
+    ("zk_mgpu_set_wait", _i, [_vp, _i]),
     ("zk_mgpu_launch_count", C.c_uint64, [_vp]),
     ("zk_mgpu_msm_vartime", _i, [_vp, _vp, _vp, _sz, _vp]),
     ("zk_mgpu_table_create", _i, [_vp, _sz, C.POINTER(_vp)]),

@@ -214,6 +214,11 @@ extern "C" int zk_mgpu_set_staging(zk_mgpu* mg, int mode) {
     for (zk_ctx* c : mg->ctx) TRY(zk_ctx_set_staging(c, mode));
     return ZK_OK;
 }
+extern "C" int zk_mgpu_set_wait(zk_mgpu* mg, int mode) {
+    if (!mg) return ZK_ERR_ARG;
+    for (zk_ctx* c : mg->ctx) TRY(zk_ctx_set_wait(c, mode));
+    return ZK_OK;
+}
 extern "C" uint64_t zk_mgpu_launch_count(const zk_mgpu* mg) {
     uint64_t s = 0;
     if (mg) for (zk_ctx* c : mg->ctx) s += c->launches;

@@ -957,6 +957,7 @@ static int ensure(zk_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+static cudaError_t wait_main(zk_ctx* ctx);
 
 extern "C" int zk_abi_version(void) { return ZK_ABI_VERSION; }
 
@@ -1007,6 +1008,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     for (int i = 0; i < ZK_STAGE_SLOTS; i++) {
         if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
@@ -1019,7 +1021,13 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
 
 extern "C" int zk_ctx_sync(zk_ctx* ctx) {
     if (!ctx) return ZK_ERR_ARG;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, wait_main(ctx));
+    return ZK_OK;
+}
+extern "C" int zk_ctx_set_wait(zk_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return ZK_ERR_ARG;
+    ctx->wait_mode = mode;
     return ZK_OK;
 }
 extern "C" void* zk_ctx_stream(zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -1055,6 +1063,20 @@ extern "C" int zk_host_unregister(void* ptr) {
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return ZK_ERR_CUDA; }
     return ZK_OK;
+}
+
+// Wait for everything queued on the ctx's main stream: spinning in cudaStreamSynchronize (default, lowest latency), or
+// parked on a blocking-sync event (zk_ctx_set_wait(ctx, 1)).  With several contexts in flight per GPU and several GPUs
+// per host, spinning waiters occupy one core each and can starve the threads that feed the copies; a blocking wait
+// costs ~0.3 ms of wake-up latency per call instead.
+static cudaError_t wait_main(zk_ctx* ctx) {
+    if (ctx->wait_mode == 0) return cudaStreamSynchronize(ctx->stream);
+    if (!ctx->ev_done) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
+    return e == cudaSuccess ? cudaEventSynchronize(ctx->ev_done) : e;
 }
 
 // ---- host -> device uploads -------------------------------------------------------------------------------------
@@ -1555,7 +1577,7 @@ static int finish_encode(zk_ctx* ctx, const void* ext_dev, size_t g, uint8_t out
     }
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, wait_main(ctx));
     memcpy(out32, ctx->h_out, 32);
     if (ctx->profiling) {
         for (int i = 0; i < 4; i++) {
@@ -1664,7 +1686,7 @@ int zk_internal_enqueue_partial(zk_ctx* ctx, const zk_host_piece* pieces, int np
 void* zk_internal_partial_ptr(zk_ctx* ctx) { return ctx->out_ext.p; }
 int zk_internal_finish_partial(zk_ctx* ctx, size_t* bad_index) {
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, wait_main(ctx));
     unsigned long long b; memcpy(&b, ctx->h_out + 32, 8);
     if (bad_index) *bad_index = b == ~0ull ? (size_t)-1 : (size_t)b;
     return b == ~0ull ? ZK_OK : ZK_ERR_INVALID_POINT;
@@ -1730,7 +1752,7 @@ static int batch_impl(zk_ctx* ctx, const uint8_t* scalars32_host, const uint8_t*
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], st));
     CK(ctx, cudaMemcpyAsync(out32s, ctx->batch_out.p, m * 32, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaMemcpyAsync(h_bad, bad_msm_dev, m * 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, wait_main(ctx));
     if (ctx->profiling) {
         for (int i = 1; i < 4; i++) {
             float ms = 0;

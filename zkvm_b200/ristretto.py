@@ -180,6 +180,10 @@ class Context:
         self._check(rc)
         return CompressedRistretto(out.raw)
 
+    def set_wait(self, mode: int):
+        """0 = spin while waiting for the device (default), 1 = block (no CPU while waiting, ~0.3 ms more latency)."""
+        self._check(self._lib.zk_ctx_set_wait(self._h, mode))
+
     def set_staging(self, mode: int):
         """0 = auto (pinned ring for pageable sources), 1 = never stage, 2 = always stage."""
         self._check(self._lib.zk_ctx_set_staging(self._h, mode))
@@ -498,8 +502,15 @@ class MultiGpu:
         self._check(rc)
         return CompressedRistretto(out.raw)
 
+    def set_wait(self, mode: int):
+        """0 = spin while waiting for the device (default), 1 = block (no CPU while waiting, ~0.3 ms more latency)."""
+        self._check(self._lib.zk_ctx_set_wait(self._h, mode))
+
     def set_staging(self, mode: int):
         self._check(self._lib.zk_mgpu_set_staging(self._h, mode))
+
+    def set_wait(self, mode: int):
+        self._check(self._lib.zk_mgpu_set_wait(self._h, mode))
 
     @property
     def launch_count(self) -> int:
