@@ -209,10 +209,6 @@ int zk_mgpu_msm_vartime_table(zk_mgpu* mg, const uint8_t* scalars32_host, const 
 /* ---- tuning / measurement ---- */
 /* Force the Pippenger window width (bits, 4..20); 0 restores the size-based choice. */
 int zk_ctx_set_window(zk_ctx* ctx, int c);
-/* The window Horner first runs with short-carry field additions and redoes itself with the exact ones if a carry was
- * dropped (probability ~2^-49 per MSM).  on = 1 skips the fast pass: same bytes, ~15 us more latency per MSM.  For tests
- * and measurement. */
-int zk_ctx_set_exact_tail(zk_ctx* ctx, int on);
 /* Window the size-based rule picks for an n-point MSM. */
 int zk_pick_window(size_t n);
 /* Integer-pipe microbenchmark: sustained 32x32+64 multiply-accumulate (IMAD.WIDE.U32 with carry)

@@ -11,18 +11,6 @@ static void st(uint8_t* b, const fe& r) { memcpy(b, r.v, 32); }
 
 extern "C" {
 // op: 0 mul, 1 sqr, 2 add, 3 sub, 4 freeze(a), 5 invert(a), 6 neg, 7 pow22523
-// short-carry add (op 0) / sub (op 1): returns the number of operations that raised the dropped-carry flag; flags[i] per op
-size_t emul_fe_short(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* flags, size_t n) {
-    size_t raised = 0;
-    for (size_t i = 0; i < n; i++) {
-        fe x, y, r; ld(x, a + 32 * i); ld(y, b + 32 * i);
-        uint32_t flag = 0;
-        if (op == 0) fe_add_short(r, x, y, flag); else fe_sub_short(r, x, y, flag);
-        st(out + 32 * i, r);
-        flags[i] = flag ? 1 : 0; raised += flag ? 1 : 0;
-    }
-    return raised;
-}
 void emul_fe_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
     for (size_t i = 0; i < n; i++) {
         fe x, y, r; ld(x, a + 32 * i); ld(y, b + 32 * i);

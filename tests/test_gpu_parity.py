@@ -161,30 +161,6 @@ def test_sum_compressed(ctx, c_oracle, rfc_vectors):
     hp.close()
 
 
-def test_exact_and_fast_tail_agree(ctx, c_oracle):
-    """The window Horner's short-carry fast pass and its exact fallback (forced with set_exact_tail) give the oracle's bytes,
-    for single MSMs and batches."""
-    import zkvm_b200 as zk
-    n = 2500
-    pts = make_points(c_oracle, n, 808); sc = rand_scalars(n, 808)
-    tab = zk.PointTable(ctx).append_compressed(pts)
-    want = c_oracle.msm(sc, pts, n, threads=4)
-    seg = np.array([0, 100, 100, 1300, n], dtype=np.uint64)
-    wantb = [c_oracle.msm(sc[int(a):int(b)], pts[32 * int(a):32 * int(b)], int(b - a)) for a, b in zip(seg, seg[1:])]
-    for exact in (True, False):
-        ctx.set_exact_tail(exact)
-        try:
-            for c in (0, 5, 9, 16):
-                ctx.set_window(c)
-                assert bytes(zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc, tab)) == want, (exact, c)
-                assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want, (exact, c)
-            ctx.set_window(0)
-            got = zk.batch_optional_multiscalar_mul(ctx, sc, pts, seg)
-            assert [bytes(g) for g in got] == wantb, exact
-        finally:
-            ctx.set_exact_tail(False); ctx.set_window(0)
-
-
 def test_invalid_point_anywhere_rejects(ctx, c_oracle, rfc_vectors):
     import zkvm_b200 as zk
     n = 2048

@@ -53,7 +53,6 @@ SYMBOLS = [
     ("zk_ctx_set_priority", _i, [_vp, _i]),
     ("zk_encoding_is_identity", _i, [_vp]),
     ("zk_ctx_set_window", _i, [_vp, _i]),
-    ("zk_ctx_set_exact_tail", _i, [_vp, _i]),
     ("zk_pick_window", _i, [_sz]),
     ("zk_bench_int_pipe", _i, [_vp, _i, C.POINTER(C.c_double)]),
     ("zk_ctx_set_profiling", _i, [_vp, _i]),

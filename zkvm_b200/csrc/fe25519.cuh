@@ -100,53 +100,6 @@ ZK_HD ZK_INLINE void fe_sub(fe& r, const fe& a, const fe& b) {
 #endif
 }
 
-// Short-carry variants for the single-warp tail (window Horner): after the 8-limb chain the wrapped carry (weight
-// 2^256 = 38) is added to limb 0 and allowed to ripple ONE limb further; a carry out of limb 1 -- probability ~2^-59 per
-// operation on the values the tail sees, but possible -- is not propagated, it sets `flag` instead, and the caller redoes
-// its whole computation with the exact routines when the flag is up.  10 dependent links instead of 19.
-ZK_HD ZK_INLINE void fe_add_short(fe& r, const fe& a, const fe& b, uint32_t& flag) {
-#if defined(__CUDA_ARCH__)
-    uint32_t c, k;
-    asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
-        "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24;"
-        "addc.u32 %8, 0, 0;"
-        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
-          "=&r"(r.v[7]), "=&r"(c)
-        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
-          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-    uint32_t m = c * 38u;
-    asm("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, 0; addc.u32 %2, 0, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "=&r"(k) : "r"(m));
-    flag |= k;
-#else
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
-    c *= 38u;
-    for (int i = 0; i < 2; i++) { c += r.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
-    flag |= (uint32_t)c;
-#endif
-}
-ZK_HD ZK_INLINE void fe_sub_short(fe& r, const fe& a, const fe& b, uint32_t& flag) {
-#if defined(__CUDA_ARCH__)
-    uint32_t c, k;
-    asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
-        "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24;"
-        "subc.u32 %8, 0, 0;"
-        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
-          "=&r"(r.v[7]), "=&r"(c)
-        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
-          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-    uint32_t m = c & 38u;   // c is 0 or 0xffffffff
-    asm("sub.cc.u32 %0, %0, %3; subc.cc.u32 %1, %1, 0; subc.u32 %2, 0, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "=&r"(k) : "r"(m));
-    flag |= k;
-#else
-    int64_t c = 0;
-    for (int i = 0; i < 8; i++) { c += (int64_t)a.v[i] - b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
-    int64_t m = c ? 38 : 0; c = 0;
-    for (int i = 0; i < 2; i++) { c += (int64_t)r.v[i] - (i == 0 ? m : 0); r.v[i] = (uint32_t)c; c >>= 32; }
-    flag |= (uint32_t)(c ? 1 : 0);
-#endif
-}
-
 ZK_HD ZK_INLINE void fe_neg(fe& r, const fe& a) { fe z = fe_zero(); fe_sub(r, z, a); }
 ZK_HD ZK_INLINE void fe_dbl(fe& r, const fe& a) { fe_add(r, a, a); }
 

@@ -44,7 +44,6 @@ struct zk_ctx {
     unsigned stage_next = 0;
     int staging_mode = 0;                   // 0 = auto (ring for pageable sources), 1 = never, 2 = always
     uint64_t staged_bytes = 0;              // bytes that went through the ring (diagnostics)
-    int exact_tail = 0;                     // 1 = the window Horner skips its short-carry fast pass (tests, measurement)
     int wait_mode = 0;                      // 0 = spin in cudaStreamSynchronize, 1 = park on a blocking-sync event
     cudaEvent_t ev_done = nullptr;          // blocking-sync event for wait_main()
 };

@@ -612,66 +612,38 @@ __device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const
 // on entry (false: X Y Z T, true: X T Z Y); the result has layout !SW.  T is not an input of a doubling.
 // Single-warp latency (tools/ubench/quad_latency.cu): 1386 cycles against 1510 for the straightforward form; exchanging
 // through shared memory instead of shuffles was measured too and is slower (1540).
-// FAST = the additions use the short-carry routines (fe_add_short): `flag` comes back nonzero if a carry was dropped
-// anywhere in the chain, in which case the caller must recompute with FAST = false.
-template <bool SW, bool FAST>
-__device__ __forceinline__ void quad_dbl_chain(fe& r, const fe& p, const quad_ctx& c, uint32_t& flag) {
+template <bool SW>
+__device__ __forceinline__ void quad_dbl_chain(fe& r, const fe& p, const quad_ctx& c) {
     const int q = c.q;
     const int lx = c.base, lz = c.base + 2, ly = c.base + (SW ? 3 : 1), lt = c.base + (SW ? 1 : 3);
     const bool isx = q == 0, isz = q == 2, isy = q == (SW ? 3 : 1), ist = q == (SW ? 1 : 3);
     fe got, s, opnd, sq, A, Bv, apb, bma, c2, L, R, val, oth, z = fe_zero();
     fe_shfl(got, p, isx ? ly : (ist ? lx : c.base + q), c.mask);     // X-holder gets Y, T-holder gets X
-    if (FAST) fe_add_short(s, p, got, flag); else fe_add(s, p, got);
+    fe_add(s, p, got);
     fe_select(opnd, p, s, isx); fe_select(opnd, opnd, got, ist);     // X+Y | Y | Z | X
     fe_sqr(sq, opnd);                                               // t | B | Z^2 | A
     fe_shfl(A, sq, lt, c.mask); fe_shfl(Bv, sq, ly, c.mask);
-    if (FAST) { fe_add_short(apb, A, Bv, flag); fe_sub_short(bma, Bv, A, flag); fe_add_short(c2, sq, sq, flag); }
-    else { fe_add(apb, A, Bv); fe_sub(bma, Bv, A); fe_add(c2, sq, sq); }
+    fe_add(apb, A, Bv); fe_sub(bma, Bv, A); fe_add(c2, sq, sq);
     fe_select(L, bma, sq, isx); fe_select(L, L, z, isy);             // t | 0 | B-A | B-A
     fe_select(R, apb, c2, isz); fe_select(R, R, z, ist);             // A+B | A+B | 2Z^2 | 0
-    if (FAST) fe_sub_short(val, L, R, flag); else fe_sub(val, L, R); // E | H | F | G   (holders of X | Y | Z | T)
+    fe_sub(val, L, R);                                              // E | H | F | G   (holders of X | Y | Z | T)
     fe_shfl(oth, val, isx ? lz : (isz ? lt : (ist ? ly : lx)), c.mask);   // E<-F, F<-G, G<-H, H<-E
     fe_mul(r, val, oth);                                            // X3 = EF | T3 = EH | Z3 = FG | Y3 = GH
 }
 // k doublings of the quad's point, standard layout in and out.
-template <bool FAST>
-__device__ __forceinline__ void quad_dbl_n_t(fe& acc, int k, const quad_ctx& c, uint32_t& flag) {
+__device__ __forceinline__ void quad_dbl_n(fe& acc, int k, const quad_ctx& c) {
 #pragma unroll 1
-    for (; k >= 2; k -= 2) { quad_dbl_chain<false, FAST>(acc, acc, c, flag); quad_dbl_chain<true, FAST>(acc, acc, c, flag); }
+    for (; k >= 2; k -= 2) { quad_dbl_chain<false>(acc, acc, c); quad_dbl_chain<true>(acc, acc, c); }
     if (k == 1) {
-        quad_dbl_chain<false, FAST>(acc, acc, c, flag);
+        quad_dbl_chain<false>(acc, acc, c);
         fe sw; fe_shfl(sw, acc, c.base + (c.q == 1 ? 3 : (c.q == 3 ? 1 : c.q)), c.mask);      // Y and T back to lanes 1 and 3
         acc = sw;
     }
 }
-// exact form (tree levels: few doublings per node, thousands of nodes)
-__device__ __forceinline__ void quad_dbl_n(fe& acc, int k, const quad_ctx& c) {
-    uint32_t unused = 0;
-    quad_dbl_n_t<false>(acc, k, c, unused);
-}
+
 __device__ __forceinline__ void quad_neg(fe& r, const fe& p, int q) { fe_cneg(r, p, q == 0 || q == 3); }
 __device__ __forceinline__ void quad_ld(fe& r, const uint4* base, size_t idx, int q) { ld_fe_plain(r, base + idx * 8 + q * 2); }
 __device__ __forceinline__ void quad_st(uint4* base, size_t idx, int q, const fe& r) { st_fe(base + idx * 8 + q * 2, r); }
-
-// Horner over one MSM's window sums: acc = sum_w 2^(off_w) wt[w], all lanes of the quad.  Runs with the short-carry
-// additions first; if any of its ~1000 additions dropped a carry (never observed; ~2^-49 per MSM) the quad recomputes
-// with the exact ones.
-template <bool FAST>
-__device__ __forceinline__ uint32_t quad_horner_t(fe& acc, const uint4* __restrict__ base, int windows, int geomW, const quad_ctx& c) {
-    fe tmp; uint32_t flag = 0;
-    quad_ld(acc, base, windows - 1, c.q);
-#pragma unroll 1
-    for (int w = windows - 2; w >= 0; w--) {
-        quad_dbl_n_t<FAST>(acc, window_geom(geomW, w).width, c, flag);
-        quad_ld(tmp, base, w, c.q);
-        quad_add(acc, acc, tmp, c);
-    }
-    return flag;
-}
-__device__ __forceinline__ void quad_horner(fe& acc, const uint4* __restrict__ base, int windows, int geomW, const quad_ctx& c, int exact_only) {
-    uint32_t flag = exact_only ? 1u : quad_horner_t<true>(acc, base, windows, geomW, c);
-    if (__any_sync(c.mask, flag != 0)) quad_horner_t<false>(acc, base, windows, geomW, c);
-}
 
 constexpr uint32_t HEAVY_PARTIALS = 24;   // a bucket with more partials than this is summed by the whole warp
 
@@ -802,13 +774,19 @@ __global__ void __launch_bounds__(128) k_tree_level_warp(const uint4* __restrict
 // Horner over the per-window sums: out[m] = sum_w 2^(off_w) * Wt[m*W + w].  One quad per MSM (253 dependent doublings).
 // `geomW` = number of digit windows the offsets come from (windows == 1 with precomputed tables: nothing to double).
 __global__ void __launch_bounds__(32) k_window_combine(const uint4* __restrict__ wt, int windows, int geomW, uint32_t nmsm,
-                                                       uint4* __restrict__ out_ext, int exact_only) {
+                                                       uint4* __restrict__ out_ext) {
     const uint32_t m = blockIdx.x * 8 + (threadIdx.x >> 2);
     if (m >= nmsm) return;
     const quad_ctx c = quad_self();
     const uint4* base = wt + (size_t)m * windows * 8;
-    fe acc;
-    quad_horner(acc, base, windows, geomW, c, exact_only);
+    fe acc, tmp;
+    quad_ld(acc, base, windows - 1, c.q);
+#pragma unroll 1
+    for (int w = windows - 2; w >= 0; w--) {
+        quad_dbl_n(acc, window_geom(geomW, w).width, c);
+        quad_ld(tmp, base, w, c.q);
+        quad_add(acc, acc, tmp, c);
+    }
     quad_st(out_ext, m, c.q, acc);
 }
 
@@ -877,12 +855,18 @@ __global__ void __launch_bounds__(256) k_sum_compressed(const uint4* __restrict_
 // Single-MSM tail in ONE launch: Horner over the window sums (one quad), then RFC 9496 Encode (one thread) -- the
 // extended result is also left in out_ext for callers that want it.  Saves a kernel boundary on the serial tail.
 __global__ void __launch_bounds__(32) k_combine_encode(const uint4* __restrict__ wt, int windows, int geomW,
-                                                       uint4* __restrict__ out_ext, uint4* __restrict__ out32, int exact_only) {
+                                                       uint4* __restrict__ out_ext, uint4* __restrict__ out32) {
     __shared__ uint4 sh[8];
     if (threadIdx.x < 4) {
         const quad_ctx c = quad_self();
-        fe acc;
-        quad_horner(acc, wt, windows, geomW, c, exact_only);
+        fe acc, tmp;
+        quad_ld(acc, wt, windows - 1, c.q);
+#pragma unroll 1
+        for (int w = windows - 2; w >= 0; w--) {
+            quad_dbl_n(acc, window_geom(geomW, w).width, c);
+            quad_ld(tmp, wt, w, c.q);
+            quad_add(acc, acc, tmp, c);
+        }
         quad_st(sh, 0, c.q, acc);
         quad_st(out_ext, 0, c.q, acc);
     }
@@ -1039,11 +1023,6 @@ extern "C" int zk_ctx_sync(zk_ctx* ctx) {
     if (!ctx) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, wait_main(ctx));
-    return ZK_OK;
-}
-extern "C" int zk_ctx_set_exact_tail(zk_ctx* ctx, int on) {
-    if (!ctx) return ZK_ERR_ARG;
-    ctx->exact_tail = on ? 1 : 0;
     return ZK_OK;
 }
 extern "C" int zk_ctx_set_wait(zk_ctx* ctx, int mode) {
@@ -1581,9 +1560,9 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
         if (m_out == 1) break;
     }
     if (fused_out32 && nmsm == 1)
-        k_combine_encode<<<1, 32, 0, st>>>(w_in, WB, W1, (uint4*)out_ext_dev, (uint4*)fused_out32, ctx->exact_tail);
+        k_combine_encode<<<1, 32, 0, st>>>(w_in, WB, W1, (uint4*)out_ext_dev, (uint4*)fused_out32);
     else
-        k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev, ctx->exact_tail);
+        k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev);
     LAUNCH_CHECK(ctx);
     return ZK_OK;
 }

@@ -153,10 +153,6 @@ class Context:
     def set_window(self, c: int):
         self._check(self._lib.zk_ctx_set_window(self._h, c))
 
-    def set_exact_tail(self, on: bool):
-        """Skip the window Horner's short-carry fast pass (same bytes; for tests and measurement)."""
-        self._check(self._lib.zk_ctx_set_exact_tail(self._h, 1 if on else 0))
-
     def set_profiling(self, on: bool):
         self._check(self._lib.zk_ctx_set_profiling(self._h, 1 if on else 0))
 
