@@ -7,7 +7,9 @@
 //   scatter         point index (+ sign bit) written at its bucket's cursor  = counting sort by bucket
 //   bucket accum    one thread per bucket walks its sorted index run, 7M mixed adds against the Niels table
 //   tree reduce     radix-8 tree per window: (A, Wt) = (plain sum, position-weighted sum) of bucket ranges
-//   window combine  Horner over windows, then RFC 9496 Encode
+//   window combine  Horner over windows + RFC 9496 Encode, one launch (k_combine_encode)
+// Host side (second half of this file): contexts and workspaces, host->device staging, the pipeline driver and the
+// single-device C ABI; the multi-GPU entry points live in mgpu.cu.
 //
 // Spec: RFC 9496 for every byte that crosses the ABI; the bucket method itself is the textbook
 // Pippenger/Bernstein algorithm (the result is algorithm-independent: the encoding of a group
