@@ -206,6 +206,11 @@ int zk_mgpu_table_append_uniform(zk_mgpu_table* t, const uint8_t* bytes64_host, 
 int zk_mgpu_msm_vartime_table(zk_mgpu* mg, const uint8_t* scalars32_host, const zk_mgpu_table* t, size_t offset,
                               size_t n, uint8_t out32[32]);
 
+/* Static prefix from the sharded cache + dynamic compressed suffix (zk_msm_vartime_mixed over all g devices). */
+int zk_mgpu_msm_vartime_mixed(zk_mgpu* mg, const uint8_t* scalars_static32_host, const zk_mgpu_table* t, size_t offset,
+                              size_t n_static, const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host,
+                              size_t n_dyn, uint8_t out32[32]);
+
 /* ---- tuning / measurement ---- */
 /* Force the Pippenger window width (bits, 4..20); 0 restores the size-based choice. */
 int zk_ctx_set_window(zk_ctx* ctx, int c);

@@ -94,6 +94,14 @@ def test_mgpu_sharded_table_slices(c_oracle):
             assert bytes(got) == c_oracle.msm(sc[off:off + m], pts[32 * off:32 * (off + m)], m, threads=2), (off, m)
         with pytest.raises(zk.ZkError):
             mg.vartime_multiscalar_mul(sc[:10], t, offset=n - 5)
+        # mixed form: a slice of the sharded cache + dynamic compressed points (bulletproofs' verification shape)
+        for off, m, nd in ((0, n, 0), (700, 3000, 77), (0, 0, 500), (n - 1, 1, 1), (1000, 1, 4099)):
+            dsc, dpt = _inputs(c_oracle, nd, 1000 + nd)
+            all_s = np.concatenate([sc[off:off + m].reshape(-1), dsc.reshape(-1)])
+            all_p = pts[32 * off:32 * (off + m)] + dpt
+            got = mg.mixed_multiscalar_mul(sc[off:off + m], t, dsc, dpt, offset=off)
+            assert bytes(got) == c_oracle.msm(all_s, all_p, m + nd, threads=2), (off, m, nd)
+        assert mg.mixed_multiscalar_mul(sc[:5], t, sc[:1], bytes([1]) + bytes(31)) is None       # s = 1 is not a valid encoding
         u = np.random.default_rng(8).integers(0, 256, size=(257, 64), dtype=np.uint8)
         t.append_uniform(u)
         up = c_oracle.from_uniform(u, 257)

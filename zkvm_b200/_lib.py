@@ -80,6 +80,7 @@ SYMBOLS = [
     ("zk_mgpu_table_append_compressed", _i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     ("zk_mgpu_table_append_uniform", _i, [_vp, _vp, _sz]),
     ("zk_mgpu_msm_vartime_table", _i, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    ("zk_mgpu_msm_vartime_mixed", _i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
 ]
 
 _lib = None

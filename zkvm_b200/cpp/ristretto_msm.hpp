@@ -206,6 +206,16 @@ class MultiGpuTable {
         mg_.check(zk_mgpu_msm_vartime_table(mg_.raw(), reinterpret_cast<const uint8_t*>(scalars), h_, offset, n, out.data()));
         return out;
     }
+    // cached generators [offset, offset + n_static) + the proof's own compressed points; nullopt if one of those is invalid
+    std::optional<CompressedRistretto> mixed_multiscalar_mul(const Scalar* static_scalars, size_t offset, size_t n_static,
+                                                             const Scalar* dyn_scalars, const CompressedRistretto* dyn_points, size_t n_dyn) {
+        CompressedRistretto out{};
+        int rc = zk_mgpu_msm_vartime_mixed(mg_.raw(), reinterpret_cast<const uint8_t*>(static_scalars), h_, offset, n_static,
+                                           reinterpret_cast<const uint8_t*>(dyn_scalars), reinterpret_cast<const uint8_t*>(dyn_points), n_dyn, out.data());
+        if (rc == ZK_ERR_INVALID_POINT) return std::nullopt;
+        mg_.check(rc);
+        return out;
+    }
   private:
     MultiGpu& mg_;
     zk_mgpu_table* h_ = nullptr;

@@ -367,32 +367,47 @@ extern "C" int zk_mgpu_table_append_uniform(zk_mgpu_table* t, const uint8_t* byt
     return mgpu_append(t, bytes64_host, n, 64, nullptr);
 }
 
-extern "C" int zk_mgpu_msm_vartime_table(zk_mgpu* mg, const uint8_t* scalars32_host, const zk_mgpu_table* t, size_t offset, size_t n,
-                                         uint8_t out32[32]) {
-    if (!mg || !t || t->mg != mg || !out32 || (n && !scalars32_host) || offset > t->len || n > t->len - offset) return ZK_ERR_ARG;
+// static part: table[offset .. offset+n_static) with scalars_static; dynamic part: n_dyn compressed encodings with their
+// scalars.  Device r takes its own rows of the slice plus the index range shard_range(n_dyn, r, g) of the dynamic terms.
+extern "C" int zk_mgpu_msm_vartime_mixed(zk_mgpu* mg, const uint8_t* scalars_static32_host, const zk_mgpu_table* t, size_t offset,
+                                         size_t n_static, const uint8_t* scalars_dyn32_host, const uint8_t* points_dyn32_host,
+                                         size_t n_dyn, uint8_t out32[32]) {
+    if (!mg || !out32) return ZK_ERR_ARG;
+    if (n_static && (!t || t->mg != mg || !scalars_static32_host || offset > t->len || n_static > t->len - offset)) return ZK_ERR_ARG;
+    if (n_dyn && (!scalars_dyn32_host || !points_dyn32_host)) return ZK_ERR_ARG;
     mg->err[0] = 0;
-    // device r: which of its local rows fall into [offset, offset+n), and which host scalar pieces feed them
+    // device r: which of its local rows fall into [offset, offset+n_static), and which host scalar pieces feed them
     std::vector<std::vector<zk_host_piece>> pieces(mg->g);
-    std::vector<size_t> row0(mg->g, 0), rows(mg->g, 0);
+    std::vector<size_t> row0(mg->g, 0), rows(mg->g, 0), dyn_lo(mg->g, 0), dyn_hi(mg->g, 0);
     for (int r = 0; r < mg->g; r++) {
         size_t local = 0; bool first = true;
-        for (const auto& s : t->segs) {
+        if (n_static) for (const auto& s : t->segs) {
             size_t a, b; shard_range(s.n, r, mg->g, &a, &b);
             size_t glo = s.base + a, ghi = s.base + b;                 // global indices of this device's rows of append s
-            size_t lo = glo > offset ? glo : offset, hi = ghi < offset + n ? ghi : offset + n;
+            size_t lo = glo > offset ? glo : offset, hi = ghi < offset + n_static ? ghi : offset + n_static;
             if (lo < hi) {
                 if (first) { row0[r] = local + (lo - glo); first = false; }
-                pieces[r].push_back({scalars32_host + (lo - offset) * 32, (hi - lo) * 32});
+                pieces[r].push_back({scalars_static32_host + (lo - offset) * 32, (hi - lo) * 32});
                 rows[r] += hi - lo;
             }
             local += b - a;
         }
+        shard_range(n_dyn, r, mg->g, &dyn_lo[r], &dyn_hi[r]);
     }
-    std::vector<size_t> base(mg->g, 0);
     int rc = run_all(mg, [&](int r) {
-        return zk_internal_enqueue_partial(mg->ctx[r], pieces[r].data(), (int)pieces[r].size(), t->shard[r], row0[r], rows[r], nullptr, nullptr, 0);
+        const size_t nd = dyn_hi[r] - dyn_lo[r];
+        return zk_internal_enqueue_partial(mg->ctx[r], pieces[r].data(), (int)pieces[r].size(), rows[r] ? t->shard[r] : nullptr, row0[r], rows[r],
+                                           nd ? scalars_dyn32_host + dyn_lo[r] * 32 : nullptr, nd ? points_dyn32_host + dyn_lo[r] * 32 : nullptr, nd);
     });
     int rc2 = rc == ZK_OK ? gather_and_encode(mg, out32) : rc;
-    int rc3 = finish_all(mg, base, nullptr);
-    return rc2 != ZK_OK ? rc2 : rc3;
+    int rc3 = finish_all(mg, dyn_lo, nullptr);
+    if (rc2 != ZK_OK) return rc2;
+    if (rc3 != ZK_OK) { memset(out32, 0, 32); return rc3; }
+    return ZK_OK;
+}
+
+extern "C" int zk_mgpu_msm_vartime_table(zk_mgpu* mg, const uint8_t* scalars32_host, const zk_mgpu_table* t, size_t offset, size_t n,
+                                         uint8_t out32[32]) {
+    if (!t) return ZK_ERR_ARG;
+    return zk_mgpu_msm_vartime_mixed(mg, scalars32_host, t, offset, n, nullptr, nullptr, 0, out32);
 }

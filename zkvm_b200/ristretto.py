@@ -529,6 +529,22 @@ class MultiGpu:
         self._check(rc)
         return CompressedRistretto(out.raw)
 
+    def mixed_multiscalar_mul(self, static_scalars, table: Optional[MultiGpuTable], dyn_scalars, dyn_points,
+                              offset: int = 0) -> Optional[CompressedRistretto]:
+        """Cached (sharded) generators first, then the proof's own compressed points; None if a dynamic encoding is invalid."""
+        hs, ns = _join32(static_scalars)
+        hd, nd = _join32(dyn_scalars)
+        hp, np_ = _join32(dyn_points)
+        if nd != np_:
+            raise ValueError("dynamic scalars/points length mismatch")
+        out = C.create_string_buffer(32)
+        rc = self._lib.zk_mgpu_msm_vartime_mixed(self._h, _ptr(hs), table._h if table is not None else None, offset, ns,
+                                                 _ptr(hd), _ptr(hp), nd, out)
+        if rc == _lib.ZK_ERR_INVALID_POINT:
+            return None
+        self._check(rc)
+        return CompressedRistretto(out.raw)
+
     def vartime_multiscalar_mul(self, scalars, table: MultiGpuTable, offset: int = 0, n: Optional[int] = None) -> CompressedRistretto:
         hs, ns = _join32(scalars)
         n = ns if n is None else n
