@@ -39,7 +39,7 @@ METRIC = "ristretto255_vartime_msm_points_per_s"
 UNIT = "points/s"
 MAC_PER_FE_MUL = 72      # 64 limb products + 8 for the 2^256 = 38 fold
 # dram__bytes_read.sum + dram__bytes_write.sum of k_bucket_accum at n = 2^20, c = 16, from one `ncu --set full` capture
-NCU_ACCUM_DRAM = {"bytes": 1.152223e9 + 59.630080e6, "source": "profiles/r02_ncu_full_k_bucket_accum.txt"}
+NCU_ACCUM_DRAM = {"bytes": 1.151180e9 + 60.714752e6, "source": "profiles/r02_ncu_full_k_bucket_accum.txt"}
 BLOCKED = "verified ZkVM tx/s: blocked, needs slingshot zkvm + bulletproofs + dalek sources (SURVEY.md section 0)"
 
 
