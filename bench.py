@@ -31,6 +31,11 @@ import sys
 import threading
 import time
 
+# Several contexts (4 streams each) are in flight per GPU; with the driver's default of 8 hardware queues their streams
+# alias and serialise falsely.  libzkmsm sets the same default when it is loaded; stated here too because the variable
+# must be in place before the process creates its CUDA context.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -605,6 +610,8 @@ def run_cuda(a):
             "config": config_for(a.log2n, world),
             "impl_config": {"window_bits": c, "windows": Wn, "inflight": F, "single_msm_latency_ms": latency_ms,
                             "pipelining": f"{F} contexts (stream + workspace each) in flight; results are collected in order, one step behind",
+                            "stream_priorities": "per context: digit sort, tree, Horner and Encode on a high-priority stream, accumulate/decode at low priority",
+                            "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                             "value_inputs": "scalars + cached decompressed points (affine Niels, 96 B) resident in HBM"},
             "parity": parity,
             "e2e": e2e,

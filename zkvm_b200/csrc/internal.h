@@ -31,6 +31,10 @@ struct zk_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     bool join_aux = false;
+    // high-priority stream for the phases after the accumulation (reduction tree, window Horner, Encode): with several
+    // contexts in flight their small, latency-bound grids must not queue behind the other contexts' bulk kernels
+    cudaStream_t tail = nullptr;
+    cudaEvent_t ev_acc = nullptr, ev_tail = nullptr, ev_pre = nullptr, ev_sort = nullptr;
     uint64_t launches = 0;
     int sm_count = 0;
     // workspace

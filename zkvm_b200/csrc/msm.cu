@@ -40,6 +40,27 @@ constexpr int REDUCE_RADIX = 1 << REDUCE_RADIX_LOG2;
 #endif
 constexpr size_t TREE_WARP_MAX_NODES = ZK_TREE_WARP_MAX;   // upper tree levels with at most this many nodes use a warp per node
 constexpr uint32_t TASK_LEN = 64;                   // longest run of entries one accumulation thread walks
+// CTA sizes of the sort / scan / tree kernels (tunables; co-scheduling them beside another context's accumulation was
+// measured and does not happen: the hardware starts CTAs of a second grid only once the first has none left to dispatch).
+#ifndef ZK_SORT_BLOCK
+#define ZK_SORT_BLOCK 256
+#endif
+#ifndef ZK_TREE_BLOCK
+#define ZK_TREE_BLOCK 128
+#endif
+#ifndef ZK_SCAN_BLOCK
+#define ZK_SCAN_BLOCK 256
+#endif
+// Stream priorities inside one context (several contexts are in flight per device):
+//   0 = everything on the context's one stream;
+//   1 = the phases after the accumulation (tree, Horner, Encode) on a high-priority stream;
+//   2 = the digit sort too: only the bulk kernels (accumulate, decode) stay at low priority, so the short, latency-bound
+//       phases of one MSM are never queued behind the multi-wave grids of the others.
+#ifndef ZK_TAIL_HP
+#define ZK_TAIL_HP 2
+#endif
+constexpr int SCAN_BLOCK = ZK_SCAN_BLOCK;           // threads per scan CTA, 4 buckets each
+constexpr int SCAN_TILE = SCAN_BLOCK * 4;
 
 // Window geometry.  A scalar (< 2^253 after reduction) is cut into W signed digits covering 254 bits; the widths are
 // balanced -- the first 254 % W windows are one bit wider than the rest -- so no window is a short stub whose points
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     }
 }
 
-// ---- scan + task planning (3 phases, 1024-bucket tiles) -----------------------------------------
+// ---- scan + task planning (3 phases, SCAN_TILE-bucket tiles) -----------------------------------------
 // Besides the exclusive scan of the bucket counts (-> offsets into `entries`), the same three passes split
 // every bucket into tasks of at most TASK_LEN entries and emit the task list SORTED BY LENGTH (longest
 // first).  One thread later runs one task, so the 32 lanes of a warp walk runs of (almost) equal length and
@@ -383,16 +404,16 @@ __device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long lon
     }
     return v;
 }
-// exclusive scan of one u64 per thread across a 256-thread block; *total = block sum
-__device__ __forceinline__ unsigned long long block_excl_scan_256(unsigned long long v, unsigned long long* total) {
-    __shared__ unsigned long long wsum[8];
+// exclusive scan of one u64 per thread across a SCAN_BLOCK-thread block; *total = block sum
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long wsum[SCAN_BLOCK / 32];
     unsigned long long inc = warp_incl_scan64(v);
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     unsigned long long off = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { unsigned long long x = wsum[k]; if (k < wid) off += x; tot += x; }
+    for (int k = 0; k < SCAN_BLOCK / 32; k++) { unsigned long long x = wsum[k]; if (k < wid) off += x; tot += x; }
     *total = tot;
     __syncthreads();
     return off + inc - v;
@@ -402,12 +423,12 @@ __device__ __forceinline__ unsigned long long pack_count(uint32_t cnt) {
 }
 
 // plan[0] = total tasks, plan[1 + len] = bins (phase 1) / cursors (phase 2 on), len = 0..TASK_LEN
-__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ counts, size_t nb,
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_tile_sums(const uint32_t* __restrict__ counts, size_t nb,
                                                         unsigned long long* __restrict__ tile_sums, uint32_t* __restrict__ plan) {
     __shared__ uint32_t s_bins[TASK_LEN + 1];
-    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_bins[i] = 0;
+    for (int i = threadIdx.x; i <= TASK_LEN; i += SCAN_BLOCK) s_bins[i] = 0;
     __syncthreads();
-    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
     unsigned long long v = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -419,19 +440,19 @@ __global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restri
             if (rem) atomicAdd(&s_bins[rem], 1u);
         }
     }
-    unsigned long long tot; block_excl_scan_256(v, &tot);
+    unsigned long long tot; block_excl_scan(v, &tot);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) if (s_bins[i]) atomicAdd(&plan[1 + i], s_bins[i]);
+    for (int i = threadIdx.x; i <= TASK_LEN; i += SCAN_BLOCK) if (s_bins[i]) atomicAdd(&plan[1 + i], s_bins[i]);
 }
-__global__ void __launch_bounds__(256) k_scan_tiles(unsigned long long* __restrict__ tile_sums, size_t ntiles, uint32_t* __restrict__ plan) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_tiles(unsigned long long* __restrict__ tile_sums, size_t ntiles, uint32_t* __restrict__ plan) {
     // single block
     __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (size_t base = 0; base < ntiles; base += 256) {
+    for (size_t base = 0; base < ntiles; base += SCAN_BLOCK) {
         size_t i = base + threadIdx.x;
         unsigned long long v = i < ntiles ? tile_sums[i] : 0ull, tot;
-        unsigned long long ex = block_excl_scan_256(v, &tot);
+        unsigned long long ex = block_excl_scan(v, &tot);
         unsigned long long cb = carry_s;
         if (i < ntiles) tile_sums[i] = cb + ex;
         __syncthreads();
@@ -445,15 +466,15 @@ __global__ void __launch_bounds__(256) k_scan_tiles(unsigned long long* __restri
     }
 }
 // writes offsets/cursor (entry positions), task_off (first partial slot of each bucket) and the sorted task list
-__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__ counts, size_t nb,
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const uint32_t* __restrict__ counts, size_t nb,
                                                     const unsigned long long* __restrict__ tile_offs, uint32_t* __restrict__ offsets,
                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ task_off,
                                                     uint32_t* __restrict__ plan, uint2* __restrict__ tasks) {
     __shared__ uint32_t s_bins[TASK_LEN + 1];
     __shared__ uint32_t s_base[TASK_LEN + 1];
-    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_bins[i] = 0;
+    for (int i = threadIdx.x; i <= TASK_LEN; i += SCAN_BLOCK) s_bins[i] = 0;
     __syncthreads();
-    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
     uint32_t cnt[4], r_full[4], r_rem[4];
     unsigned long long sum = 0;
 #pragma unroll
@@ -465,8 +486,8 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t* __restrict__
         r_rem[k] = rem ? atomicAdd(&s_bins[rem], 1u) : 0u;
     }
     unsigned long long tot;
-    unsigned long long ex = block_excl_scan_256(sum, &tot) + tile_offs[blockIdx.x];   // has a __syncthreads
-    for (int i = threadIdx.x; i <= TASK_LEN; i += 256) s_base[i] = s_bins[i] ? atomicAdd(&plan[1 + i], s_bins[i]) : 0u;
+    unsigned long long ex = block_excl_scan(sum, &tot) + tile_offs[blockIdx.x];   // has a __syncthreads
+    for (int i = threadIdx.x; i <= TASK_LEN; i += SCAN_BLOCK) s_base[i] = s_bins[i] ? atomicAdd(&plan[1 + i], s_bins[i]) : 0u;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -961,6 +982,13 @@ static int ensure(zk_ctx* ctx, DevBuf& b, size_t bytes) {
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 static cudaError_t wait_main(zk_ctx* ctx);
 
+// Every context owns four streams (main, two decode side streams, the high-priority one) and callers keep several
+// contexts in flight; the driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8), and streams
+// that share a queue serialise falsely (measured: 6 contexts in flight 2.67 ms/step with 8 queues, 1.52 with 32).  The
+// variable is only read when the process creates its CUDA context, so set a default when the library is loaded; an
+// explicit setting by the application wins.
+__attribute__((constructor)) static void zk_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 extern "C" int zk_abi_version(void) { return ZK_ABI_VERSION; }
 
 extern "C" const char* zk_status_str(int s) {
@@ -987,6 +1015,17 @@ extern "C" int zk_ctx_create(int device, zk_ctx** out) {
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+#if ZK_TAIL_HP
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->tail, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_acc, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_sort, cudaEventDisableTiming);
+    }
+#endif
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_out, 64);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
@@ -1017,6 +1056,11 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     }
     for (int i = 0; i < 2; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->tail) { cudaStreamSynchronize(ctx->tail); cudaStreamDestroy(ctx->tail); }
+    if (ctx->ev_acc) cudaEventDestroy(ctx->ev_acc);
+    if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
+    if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
+    if (ctx->ev_sort) cudaEventDestroy(ctx->ev_sort);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1038,7 +1082,15 @@ extern "C" int zk_ctx_set_window(zk_ctx* ctx, int c) {
     ctx->forced_window = c;
     return ZK_OK;
 }
-extern "C" int zk_ctx_set_profiling(zk_ctx* ctx, int on) { if (!ctx) return ZK_ERR_ARG; ctx->profiling = on; return ZK_OK; }
+extern "C" int zk_ctx_set_profiling(zk_ctx* ctx, int on) {
+    if (!ctx) return ZK_ERR_ARG;
+    ctx->profiling = on;
+#ifdef ZK_TIMELINE
+    extern void zk_timeline_ref(zk_ctx*);
+    if (on) zk_timeline_ref(ctx);
+#endif
+    return ZK_OK;
+}
 extern "C" int zk_ctx_last_phase_ms(zk_ctx* ctx, float out_ms[4]) {
     if (!ctx || !out_ms) return ZK_ERR_ARG;
     for (int i = 0; i < 4; i++) out_ms[i] = ctx->phase_ms[i];
@@ -1470,7 +1522,7 @@ static int msm_plan(zk_ctx* ctx, size_t n, size_t nmsm, const Precomp* pc, MsmPl
     p->B = (size_t)1 << (p->c - 1);
     p->NB = p->B * p->W;
     if (p->NB >= (1ull << 31)) return ZK_ERR_ARG;
-    p->ntiles = (p->NB + 1023) / 1024;
+    p->ntiles = (p->NB + SCAN_TILE - 1) / SCAN_TILE;
     if ((unsigned long long)n * p->W1 >= (1ull << 32)) return ZK_ERR_ARG;   // entry positions are 32-bit: shard larger MSMs
     p->max_tasks = p->NB + (n * (size_t)p->W1) / TASK_LEN;
     p->m1 = (p->B + REDUCE_RADIX - 1) / REDUCE_RADIX;
@@ -1514,23 +1566,35 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
     if (p.use_pc) { tab_a = p.pc.base; tab_b = p.pc.base; split = (size_t)0xffffffffu; }
 
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[1], st));
+#if ZK_TAIL_HP >= 2
+    // the digit sort also runs on the high-priority stream: only the bulk kernels (accumulate, decode) stay at low priority
+    cudaStream_t st_bulk = st;
+    CK(ctx, cudaEventRecord(ctx->ev_pre, st));
+    CK(ctx, cudaStreamWaitEvent(ctx->tail, ctx->ev_pre, 0));
+    st = ctx->tail;
+#endif
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, NB * 4, st));
     CK(ctx, cudaMemsetAsync(ctx->plan.p, 0, (TASK_LEN + 2) * 4, st));
-    k_digit_hist<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, win_stride, (uint32_t*)ctx->counts.p);
+    k_digit_hist<<<grid_for(n, ZK_SORT_BLOCK), ZK_SORT_BLOCK, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, win_stride, (uint32_t*)ctx->counts.p);
     LAUNCH_CHECK(ctx);
-    k_scan_tile_sums<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (unsigned long long*)ctx->tiles.p,
+    k_scan_tile_sums<<<(unsigned)ntiles, SCAN_BLOCK, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (unsigned long long*)ctx->tiles.p,
                                                         (uint32_t*)ctx->plan.p);
     LAUNCH_CHECK(ctx);
-    k_scan_tiles<<<1, 256, 0, st>>>((unsigned long long*)ctx->tiles.p, ntiles, (uint32_t*)ctx->plan.p);
+    k_scan_tiles<<<1, SCAN_BLOCK, 0, st>>>((unsigned long long*)ctx->tiles.p, ntiles, (uint32_t*)ctx->plan.p);
     LAUNCH_CHECK(ctx);
-    k_scan_apply<<<(unsigned)ntiles, 256, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (const unsigned long long*)ctx->tiles.p,
+    k_scan_apply<<<(unsigned)ntiles, SCAN_BLOCK, 0, st>>>((const uint32_t*)ctx->counts.p, NB, (const unsigned long long*)ctx->tiles.p,
                                                     (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->task_off.p,
                                                     (uint32_t*)ctx->plan.p, (uint2*)ctx->tasks.p);
     LAUNCH_CHECK(ctx);
-    k_digit_scatter<<<grid_for(n, 256), 256, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0, win_stride,
+    k_digit_scatter<<<grid_for(n, ZK_SORT_BLOCK), ZK_SORT_BLOCK, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0, win_stride,
                                                        (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
+#if ZK_TAIL_HP >= 2
+    CK(ctx, cudaEventRecord(ctx->ev_sort, st));
+    st = st_bulk;
+    CK(ctx, cudaStreamWaitEvent(st, ctx->ev_sort, 0));
+#endif
 
     if (ctx->join_aux) {          // the point table is being produced on the side streams
         for (int i = 0; i < 2; i++) CK(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
@@ -1544,6 +1608,14 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
     LAUNCH_CHECK(ctx);
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[3], st));
 
+    // the phases after the accumulation run on the context's high-priority stream (when it has one), ordered after
+    // the accumulation by an event, and the main stream is made to wait for them: callers still see one stream
+    cudaStream_t st_main = st;
+    if (ctx->tail) {
+        CK(ctx, cudaEventRecord(ctx->ev_acc, st));
+        CK(ctx, cudaStreamWaitEvent(ctx->tail, ctx->ev_acc, 0));
+        st = ctx->tail;
+    }
     // radix-8 tree, per window, until one node is left
     const uint4* a_in = (const uint4*)ctx->partials.p;
     const uint4* w_in = nullptr;
@@ -1554,9 +1626,9 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
         uint4* a_out = (uint4*)ctx->tree_a.p + (size_t)half * m1 * W * 8;
         uint4* w_out = (uint4*)ctx->tree_w.p + (size_t)half * m1 * W * 8;
         if (toff == nullptr && m_out * W <= TREE_WARP_MAX_NODES)      // few nodes: latency-bound, spend lanes on depth
-            k_tree_level_warp<<<grid_for(m_out * W * 32, 128), 128, 0, st>>>(a_in, w_in, m_in, m_out, (int)W, log2_wc, a_out, w_out);
+            k_tree_level_warp<<<grid_for(m_out * W * 32, ZK_TREE_BLOCK), ZK_TREE_BLOCK, 0, st>>>(a_in, w_in, m_in, m_out, (int)W, log2_wc, a_out, w_out);
         else
-            k_tree_level_quad<<<grid_for(m_out * W * 4, 128), 128, 0, st>>>(a_in, w_in, toff, m_in, m_out, (int)W, log2_wc, a_out, w_out);
+            k_tree_level_quad<<<grid_for(m_out * W * 4, ZK_TREE_BLOCK), ZK_TREE_BLOCK, 0, st>>>(a_in, w_in, toff, m_in, m_out, (int)W, log2_wc, a_out, w_out);
         LAUNCH_CHECK(ctx);
         a_in = a_out; w_in = w_out; toff = nullptr; m_in = m_out; log2_wc += REDUCE_RADIX_LOG2; half ^= 1;
         if (m_out == 1) break;
@@ -1566,6 +1638,10 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
     else
         k_window_combine<<<grid_for(nmsm, 8), 32, 0, st>>>(w_in, WB, W1, (uint32_t)nmsm, (uint4*)out_ext_dev);
     LAUNCH_CHECK(ctx);
+    if (ctx->tail) {
+        CK(ctx, cudaEventRecord(ctx->ev_tail, st));
+        CK(ctx, cudaStreamWaitEvent(st_main, ctx->ev_tail, 0));
+    }
     return ZK_OK;
 }
 
@@ -1601,12 +1677,34 @@ extern "C" int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk
     return msm_enqueue(ctx, plan, scalars32_dev, t->d + offset * 6, nullptr, n, out_ext128_dev);
 }
 
+#ifdef ZK_TIMELINE
+// Developer build only (-DZK_TIMELINE): with profiling on, every zk_msm_table_dev + zk_ext_sum_compress_dev pair prints
+// its phase boundaries (call, sort start, sort end, accumulate end, tree + tail end) in ms since a process-wide
+// reference event -- a timeline of several contexts in flight without a tracing tool.
+static cudaEvent_t g_tl_ref; static bool g_tl_set = false;
+#endif
+#ifdef ZK_TIMELINE
+void zk_timeline_ref(zk_ctx* ctx) {
+    if (g_tl_set) return;
+    cudaEventCreate(&g_tl_ref); cudaEventRecord(g_tl_ref, ctx->stream); cudaEventSynchronize(g_tl_ref); g_tl_set = true;
+}
+#endif
 extern "C" int zk_ext_sum_compress_dev(zk_ctx* ctx, const void* ext128_dev, size_t g, uint8_t out32[32]) {
     if (!ctx || (!ext128_dev && g) || !out32) return ZK_ERR_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     int prof = ctx->profiling; ctx->profiling = 0;
+#ifdef ZK_TIMELINE
+    if (prof) cudaEventRecord(ctx->ev[4], ctx->stream);
+#endif
     int rc = finish_encode(ctx, ext128_dev, g, out32);
     ctx->profiling = prof;
+#ifdef ZK_TIMELINE
+    if (prof && g_tl_set) {
+        float t[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], g_tl_ref, ctx->ev[i]);
+        fprintf(stderr, "TL %p %.4f %.4f %.4f %.4f %.4f\n", (void*)ctx, t[0], t[1], t[2], t[3], t[4]);
+    }
+#endif
     return rc;
 }
 
