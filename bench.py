@@ -205,6 +205,7 @@ def run_cuda(a):
     ctxs = [zk.Context(local) for _ in range(max(F, FE))]       # `value` uses the first F, the e2e loop the first FE
     ctx = ctxs[0]
     streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    gather_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in ctxs] if world > 1 else []
     n = 1 << a.log2n
     K, W = a.steps, max(a.warmup, 3)
 
@@ -245,8 +246,12 @@ def run_cuda(a):
             f, s = i % F, i % len(tabs)
             ctxs[f].msm_table_dev(scals[s].data_ptr(), tabs[s], 0, count, parts[f].data_ptr())
             if world > 1:
-                with torch.cuda.stream(streams[f]):
+                # the 128-byte gather is latency-critical and tiny: issue it at high priority, ordered after the MSM and
+                # before whatever the context's stream does next, so it is not queued behind other contexts' bulk grids
+                gather_streams[f].wait_stream(streams[f])
+                with torch.cuda.stream(gather_streams[f]):
                     dist.all_gather_into_tensor(gathered[f], parts[f].view(1, PARTIAL_BYTES))
+                streams[f].wait_stream(gather_streams[f])
 
         def collect(i):
             """Finish step i: sum the partial(s), encode, read the 32 bytes back (synchronises that context only)."""

@@ -539,3 +539,39 @@ def test_argument_errors_and_context_reuse(ctx, c_oracle):
         b = zk.RistrettoPoint.vartime_multiscalar_mul(c2, sc, t2)
         assert bytes(a) == bytes(b)
     t2.close(); c2.close()
+
+
+# ---------------- several contexts in flight (stream priorities, shared device) ----------------
+def test_contexts_in_flight_match_oracle(c_oracle):
+    """Six contexts keep MSMs of different sizes in flight on one device from six host threads (the end-to-end shape:
+    each context runs its sort / tree / tail on its high-priority stream and its bulk kernels at low priority, and they
+    all share the SMs); every result must equal the oracle's on the same bytes, and a context must stay usable."""
+    from concurrent.futures import ThreadPoolExecutor
+    import zkvm_b200 as zk
+    sizes = [1, 37, 1000, 4096, 30000, 70000]
+    jobs = []
+    for k, n in enumerate(sizes):
+        pts = make_points(c_oracle, n, 900 + k)
+        sc = rand_scalars(n, 900 + k)
+        jobs.append((n, sc, pts, c_oracle.msm(sc, pts, n, threads=4)))
+    ctxs = [zk.Context(0) for _ in sizes]
+    tabs = [zk.PointTable(ctxs[k], n).append_compressed(jobs[k][2]) for k, (n, *_r) in enumerate(jobs)]
+
+    def worker(k):
+        n, sc, pts, want = jobs[k]
+        out = []
+        for rep in range(6):
+            got = zk.RistrettoPoint.optional_multiscalar_mul(ctxs[k], sc, pts) if rep % 2 == 0 else \
+                zk.RistrettoPoint.vartime_multiscalar_mul(ctxs[k], sc, tabs[k])
+            out.append(got is not None and bytes(got) == want)
+        return out
+
+    with ThreadPoolExecutor(max_workers=len(sizes)) as pool:
+        results = list(pool.map(worker, range(len(sizes))))
+    assert all(all(r) for r in results), results
+    # and every context, one after the other, over the same cached table
+    n, sc, pts, want = jobs[-1]
+    outs = [zk.RistrettoPoint.vartime_multiscalar_mul(cx, sc, tabs[-1]) for cx in ctxs]
+    assert all(bytes(o) == want for o in outs)
+    for t in tabs: t.close()
+    for cx in ctxs: cx.close()
