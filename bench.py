@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="points per GPU (default 2^20, the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window", type=int, default=0, help="tuning only: force the Pippenger window width (0 = the library's rule)")
     ap.add_argument("--no-extras", action="store_true", help="skip sweep / strong / batch / shapes (headline numbers only)")
     ap.add_argument("--e2e-threads", type=int, default=0,
                     help="host threads of the end-to-end loop (0 = one per context in flight, fewer when cores are scarce and spinning)")
@@ -204,6 +205,8 @@ def run_cuda(a):
     FE = a.e2e_threads if a.e2e_threads > 0 else F   # blocked callers cost no CPU, so scarce cores do not limit their number
     ctxs = [zk.Context(local) for _ in range(max(F, FE))]       # `value` uses the first F, the e2e loop the first FE
     ctx = ctxs[0]
+    if a.window:
+        for cx in ctxs: cx.set_window(a.window)
     streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
     gather_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in ctxs] if world > 1 else []
     n = 1 << a.log2n
@@ -373,7 +376,7 @@ def run_cuda(a):
         if i >= 1: acc_ms.append(phases[2])
     ctx.set_profiling(False)
     acc_ms = sum(acc_ms) / len(acc_ms)
-    c = zk.pick_window(n); Wn = (254 + c - 1) // c
+    c = a.window or zk.pick_window(n); Wn = (254 + c - 1) // c
     adds = n * Wn * (1.0 - 2.0 ** -c)                       # entries = nonzero digits
     nbuckets = Wn * (1 << (c - 1))                          # ~every bucket is non-empty at this density: one task each,
     # whose first entry costs 1 multiply (ge_from_niels), every other entry a 7-multiply mixed add

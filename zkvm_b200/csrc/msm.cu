@@ -559,7 +559,13 @@ k_bucket_accum(const uint4* __restrict__ tab_a, const uint4* __restrict__ tab_b,
         ge_madd(acc, acc, q, (e >> 31) != 0);
     }
 #endif
-    st_ext(partials, task_off[d.x] + d.y, acc);
+    // stored in cached form (Y-X, Y+X, 2Z, 2dT): the tree's leaf level adds every partial into a running sum, and an
+    // addition whose second operand is cached costs two multiplication rounds instead of three
+    {
+        ge_ext cch; const fe d2 = fe_d2();
+        fe_sub(cch.X, acc.Y, acc.X); fe_add(cch.Y, acc.Y, acc.X); fe_dbl(cch.Z, acc.Z); fe_mul(cch.T, acc.T, d2);
+        st_ext(partials, task_off[d.x] + d.y, cch);
+    }
 }
 
 // ---- radix-8 reduction tree ---------------------------------------------------------------------
@@ -601,15 +607,12 @@ __device__ __forceinline__ void quad_finish(fe& r, const fe& val, const quad_ctx
     fe_select(x, val, m2, c.q == 3);
     fe_mul(r, x, m1);
 }
-// r = p + qq (both in quad layout).  Unified a = -1 addition, complete.
-__device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const quad_ctx& c) {
+// The second operand of an addition in "cached" form: (Y2-X2 | Y2+X2 | 2 Z2 | 2d T2) in lanes 0..3.
+__device__ __forceinline__ void quad_to_cached(fe& v, const fe& qq, const quad_ctx& c) {
     const int q = c.q;
     const bool l0 = q == 0, hi = q >= 2;
-    fe op, oq, a, b, dif, sum, u, v;
-    fe_shfl_xor(op, p, 1, c.mask); fe_shfl_xor(oq, qq, 1, c.mask);
-    fe_select(a, p, op, l0); fe_select(b, op, p, l0);          // lanes 0/1: a = Y1, b = X1
-    fe_sub(dif, a, b); fe_add(sum, a, b);
-    fe_select(u, sum, dif, l0); fe_select(u, u, p, hi);         // Y1-X1 | Y1+X1 | Z1 | T1
+    fe oq, a, b, dif, sum;
+    fe_shfl_xor(oq, qq, 1, c.mask);
     fe_select(a, qq, oq, l0); fe_select(b, oq, qq, l0);
     fe_sub(dif, a, b); fe_add(sum, a, b);
     fe_select(v, sum, dif, l0); fe_select(v, v, qq, hi);        // Y2-X2 | Y2+X2 | Z2 | T2
@@ -617,6 +620,16 @@ __device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const
 #pragma unroll
     for (int i = 0; i < 8; i++) k.v[i] = q == 3 ? k.v[i] : (i == 0 ? (q == 2 ? 2u : 1u) : 0u);
     fe_mul(v, v, k);                                            // ... | ... | 2 Z2 | 2d T2
+}
+// r = p + (the point whose cached form is v).  Two multiplication rounds.  Unified a = -1 addition, complete.
+__device__ __forceinline__ void quad_add_cached(fe& r, const fe& p, const fe& v, const quad_ctx& c) {
+    const int q = c.q;
+    const bool l0 = q == 0, hi = q >= 2;
+    fe op, a, b, dif, sum, u;
+    fe_shfl_xor(op, p, 1, c.mask);
+    fe_select(a, p, op, l0); fe_select(b, op, p, l0);          // lanes 0/1: a = Y1, b = X1
+    fe_sub(dif, a, b); fe_add(sum, a, b);
+    fe_select(u, sum, dif, l0); fe_select(u, u, p, hi);         // Y1-X1 | Y1+X1 | Z1 | T1
     fe r1, o;
     fe_mul(r1, u, v);                                           // A | B | D | C
     fe_shfl_xor(o, r1, 1, c.mask);
@@ -625,6 +638,11 @@ __device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const
     fe_sub(dif, a, b);                                          // lane0: B-A = E, lane2: D-C = F
     fe val; fe_select(val, dif, sum, (q & 1) != 0);             // lane1: B+A = H, lane3: D+C = G
     quad_finish(r, val, c);
+}
+// r = p + qq (both in quad layout): three multiplication rounds.
+__device__ __forceinline__ void quad_add(fe& r, const fe& p, const fe& qq, const quad_ctx& c) {
+    fe v; quad_to_cached(v, qq, c);
+    quad_add_cached(r, p, v, c);
 }
 // r = 2p, for chains of doublings (window Horner, the tree's weight shifts).  Compared with the straightforward lane
 // assignment (every lane squares its own coordinate, lane 3 squares X+Y, t/A/B broadcast, two fetches before the final
@@ -670,23 +688,20 @@ __device__ __forceinline__ void quad_st(uint4* base, size_t idx, int q, const fe
 
 constexpr uint32_t HEAVY_PARTIALS = 24;   // a bucket with more partials than this is summed by the whole warp
 
-// Leaf-level child = bucket `idx`: the sum of its tasks' partials (identity when it has none).  Called by all 32
-// lanes at the same loop trip (valid = false for a quad without a child).  A bucket that was split into many tasks
-// -- adversarial scalars put up to n / TASK_LEN partials in ONE bucket -- is reduced by the 8 quads of the warp
-// together: strided partial sums, then a butterfly over quads.
-__device__ __forceinline__ void quad_load_bucket(fe& r, const uint4* __restrict__ partials, const uint32_t* __restrict__ task_off,
-                                                 size_t idx, bool valid, const quad_ctx& c) {
+// Leaf level: run += bucket `idx`, i.e. every partial sum the accumulation left for that bucket (none: nothing to add).
+// The partials are stored in cached form (k_bucket_accum), so each costs a two-round addition straight into the running
+// sum.  Called by all 32 lanes at the same loop trip (valid = false for a quad without a child).  A bucket that was
+// split into many tasks -- adversarial scalars put up to n / TASK_LEN partials in ONE bucket -- is reduced by the 8
+// quads of the warp together: strided partial sums, then a butterfly over quads.
+__device__ __forceinline__ void quad_add_bucket(fe& run, const uint4* __restrict__ partials, const uint32_t* __restrict__ task_off,
+                                                size_t idx, bool valid, const quad_ctx& c) {
     uint32_t p0 = 0, p1 = 0;
     if (valid) { p0 = task_off[idx]; p1 = task_off[idx + 1]; }
     const bool heavy = p1 - p0 > HEAVY_PARTIALS;
     fe tmp;
     if (!heavy) {
-        if (p0 == p1) quad_identity(r, c.q);
-        else {
-            quad_ld(r, partials, p0, c.q);
 #pragma unroll 1
-            for (uint32_t p = p0 + 1; p < p1; p++) { quad_ld(tmp, partials, p, c.q); quad_add(r, r, tmp, c); }
-        }
+        for (uint32_t p = p0; p < p1; p++) { quad_ld(tmp, partials, p, c.q); quad_add_cached(run, run, tmp, c); }
     }
     unsigned hmask = __ballot_sync(0xffffffffu, heavy);          // warp-wide rendezvous
     const int lane = threadIdx.x & 31;
@@ -696,10 +711,11 @@ __device__ __forceinline__ void quad_load_bucket(fe& r, const uint4* __restrict_
         uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
         fe part; quad_identity(part, c.q);
 #pragma unroll 1
-        for (uint32_t p = q0 + (lane >> 2); p < q1; p += 8) { quad_ld(tmp, partials, p, c.q); quad_add(part, part, tmp, c); }
+        for (uint32_t p = q0 + (lane >> 2); p < q1; p += 8) { quad_ld(tmp, partials, p, c.q); quad_add_cached(part, part, tmp, c); }
 #pragma unroll 1
         for (int o = 16; o >= 4; o >>= 1) { fe_shfl_xor(tmp, part, o, 0xffffffffu); quad_add(part, part, tmp, full); }
-        if ((lane & ~3) == (src & ~3)) r = part;
+        fe sum; quad_add(sum, run, part, c);                     // every quad computes, only the owner keeps
+        if ((lane & ~3) == (src & ~3)) run = sum;
     }
 }
 
@@ -730,8 +746,7 @@ __global__ void __launch_bounds__(128, ZK_TREE_MINBLOCKS) k_tree_level_quad(cons
         for (int jj = REDUCE_RADIX - 1; jj >= 0; jj--) {
             size_t j = first + jj;
             bool valid = active && j < m_in;
-            quad_load_bucket(tmp, a_in, task_off, w * m_in + j, valid, c);
-            quad_add(run, run, tmp, c);
+            quad_add_bucket(run, a_in, task_off, w * m_in + j, valid, c);
             quad_add(acc, acc, run, c);
         }
     } else {
