@@ -14,6 +14,10 @@ ncu --set full --import-source on --clock-control none -k regex:k_bucket_accum -
     python tools/profile_msm.py 20 1 > $out/${tag}_ncu_accum.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_decompress -c 1 -f -o $out/${tag}_decompress \
     python tools/profile_msm.py 20 1 > $out/${tag}_ncu_decompress.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_digit_scatter -c 1 -f -o $out/${tag}_scatter \
+    python tools/profile_msm.py 20 1 > $out/${tag}_ncu_scatter.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_tree_level_quad -c 1 -f -o $out/${tag}_leaf \
+    python tools/profile_msm.py 20 1 > $out/${tag}_ncu_leaf.log 2>&1
 ncu --cache-control none --clock-control none --metrics gpu__time_duration.sum --csv --log-file $out/${tag}_launches_msm_2e20_warm.csv \
     python tools/profile_msm.py 20 4 > /dev/null 2>&1
 for l in 10 16; do

@@ -51,6 +51,9 @@ constexpr uint32_t TASK_LEN = 64;                   // longest run of entries on
 #ifndef ZK_SCAN_BLOCK
 #define ZK_SCAN_BLOCK 256
 #endif
+#ifndef ZK_SCATTER_BATCH
+#define ZK_SCATTER_BATCH 8                          // returning atomics a scatter thread keeps in flight
+#endif
 // Stream priorities inside one context (several contexts are in flight per device):
 //   0 = everything on the context's one stream;
 //   1 = the phases after the accumulation (tree, Horner, Encode) on a high-priority stream;
@@ -371,11 +374,11 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     size_t wbase = (size_t)m * wpm;
     // the point of term i: the i-th point, or (every MSM of the batch runs over the SAME points) the (i - seg[m])-th
     uint32_t pidx = shared_points ? (uint32_t)i - seg[m] : (uint32_t)i;
-    // 8 windows at a time: the 8 returning atomics are issued back to back, then the 8 stores
-    for (int w0 = 0; w0 < W; w0 += 8) {
-        uint32_t pos[8], val[8];
+    // ZK_SCATTER_BATCH windows at a time: their returning atomics are issued back to back, then the stores
+    for (int w0 = 0; w0 < W; w0 += ZK_SCATTER_BATCH) {
+        uint32_t pos[ZK_SCATTER_BATCH], val[ZK_SCATTER_BATCH];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < ZK_SCATTER_BATCH; k++) {
             int w = w0 + k;
             int d = w < W ? next_digit(s, window_geom(W, w), carry) : 0;
             // precomputed mode: window w of point p is row w*win_stride + p of the expanded table (= 2^(c*w) * P)
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
             pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + (win_stride ? 0 : w)) * B + (abs(d) - 1)], 1u) : 0u;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
+        for (int k = 0; k < ZK_SCATTER_BATCH; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
     }
 }
 
@@ -1665,8 +1668,20 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
 static int finish_encode(zk_ctx* ctx, const void* ext_dev, size_t g, uint8_t out32[32]) {
     TRY(ensure(ctx, ctx->out32, 32));
     if (ext_dev) {
-        k_ext_sum_encode<<<1, 32, 0, ctx->stream>>>((const uint4*)ext_dev, g, (uint4*)ctx->out32.p);
+        // one warp of latency-bound work: on the high-priority stream, so that it does not wait for a free CTA slot
+        // behind other contexts' bulk grids
+        cudaStream_t s = ctx->stream;
+        if (ctx->tail) {
+            CK(ctx, cudaEventRecord(ctx->ev_pre, ctx->stream));
+            CK(ctx, cudaStreamWaitEvent(ctx->tail, ctx->ev_pre, 0));
+            s = ctx->tail;
+        }
+        k_ext_sum_encode<<<1, 32, 0, s>>>((const uint4*)ext_dev, g, (uint4*)ctx->out32.p);
         LAUNCH_CHECK(ctx);
+        if (ctx->tail) {
+            CK(ctx, cudaEventRecord(ctx->ev_tail, s));
+            CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));
+        }
     }
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->out32.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
