@@ -44,7 +44,23 @@ METRIC = "ristretto255_vartime_msm_points_per_s"
 UNIT = "points/s"
 MAC_PER_FE_MUL = 72      # 64 limb products + 8 for the 2^256 = 38 fold
 # dram__bytes_read.sum + dram__bytes_write.sum of k_bucket_accum at n = 2^20, c = 16, from one `ncu --set full` capture
-NCU_ACCUM_DRAM = {"bytes": 1.151180e9 + 60.714752e6, "source": "profiles/r02_ncu_full_k_bucket_accum.txt"}
+NCU_ACCUM_SUMMARY = "profiles/r02_ncu_full_k_bucket_accum.txt"   # written by tools/summarise_ncu.py from the .ncu-rep
+
+
+def ncu_accum_dram():
+    """DRAM bytes (read + write) of one k_bucket_accum launch, parsed from the committed ncu summary of this build."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    try:
+        for line in open(os.path.join(ROOT, NCU_ACCUM_SUMMARY)):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1].replace(",", "")) * unit[f[2]]; seen += 1
+    except (OSError, KeyError, ValueError):
+        return None
+    return {"bytes": tot, "source": NCU_ACCUM_SUMMARY} if seen == 2 else None
+
+
 BLOCKED = "verified ZkVM tx/s: blocked, needs slingshot zkvm + bulletproofs + dalek sources (SURVEY.md section 0)"
 
 
@@ -601,7 +617,8 @@ def run_cuda(a):
         try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception: pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        traffic = NCU_ACCUM_DRAM["bytes"] if (a.log2n == 20 and c == 16) else None
+        NCU_ACCUM_DRAM = ncu_accum_dram() if (a.log2n == 20 and c == 16) else None
+        traffic = NCU_ACCUM_DRAM["bytes"] if NCU_ACCUM_DRAM else None
         parity["ok"] = all(parity["paths"].values())
         parity["oracle_seconds"] = oracle_s
         e2e = {"value": n * world * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,

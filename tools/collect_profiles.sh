@@ -6,12 +6,15 @@
 tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
+# the dominant kernel first: bench.py reports its DRAM traffic from the summary of THIS build
+ncu --set full --import-source on --clock-control none -k regex:k_bucket_accum -c 1 -f -o $out/${tag}_accum \
+    python tools/profile_msm.py 20 1 > $out/${tag}_ncu_accum.log 2>&1
+python tools/summarise_ncu.py $out/${tag}_accum.ncu-rep k_bucket_accum > profiles/r02_ncu_full_k_bucket_accum.txt
+cp profiles/r02_ncu_full_k_bucket_accum.txt $out/${tag}_ncu_full_k_bucket_accum.txt
 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err
 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_cpu.json 2> $out/${tag}_bench_reference_cpu.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_bench_steps2_warmup3.csv \
     python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:k_bucket_accum -c 1 -f -o $out/${tag}_accum \
-    python tools/profile_msm.py 20 1 > $out/${tag}_ncu_accum.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_decompress -c 1 -f -o $out/${tag}_decompress \
     python tools/profile_msm.py 20 1 > $out/${tag}_ncu_decompress.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_digit_scatter -c 1 -f -o $out/${tag}_scatter \
