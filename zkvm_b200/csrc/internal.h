@@ -31,8 +31,10 @@ struct zk_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     bool join_aux = false;
-    // high-priority stream for the phases after the accumulation (reduction tree, window Horner, Encode): with several
-    // contexts in flight their small, latency-bound grids must not queue behind the other contexts' bulk kernels
+    // high-priority stream for the short, latency-bound phases (digit sort, reduction tree, window Horner, Encode): with
+    // several contexts in flight their grids must not queue behind the other contexts' bulk kernels (accumulate, decode),
+    // which stay on the low-priority main / side streams.  The phases hop between the two through these events; the main
+    // stream always waits for the hop back, so callers see one stream (msm.cu: ZK_TAIL_HP).
     cudaStream_t tail = nullptr;
     cudaEvent_t ev_acc = nullptr, ev_tail = nullptr, ev_pre = nullptr, ev_sort = nullptr;
     uint64_t launches = 0;
