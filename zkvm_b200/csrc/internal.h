@@ -30,6 +30,7 @@ struct zk_ctx {
     // main stream uploads the scalars and sorts digits; the main stream joins them right before the accumulation
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_scan = nullptr;          // histogram + scan done: a decoder that scatters its own terms may start
     bool join_aux = false;
     // high-priority stream for the short, latency-bound phases (digit sort, reduction tree, window Horner, Encode): with
     // several contexts in flight their grids must not queue behind the other contexts' bulk kernels (accumulate, decode),

@@ -123,6 +123,23 @@ __device__ __forceinline__ uint32_t segment_of(const uint32_t* __restrict__ seg,
 #ifndef ZK_DEC_PAIR
 #define ZK_DEC_PAIR 0   // measured: 2.16 ms vs 1.98 ms at 2^20 (205 registers halve the occupancy); kept for the record
 #endif
+// One thread: encoding i of `in` -> affine-Niels row i of `table` (identity + reject flags when it does not decode).
+__device__ __forceinline__ void decompress_one(const uint4* __restrict__ in, size_t i, uint4* __restrict__ table,
+                                               unsigned long long* __restrict__ bad, unsigned long long index_base,
+                                               const uint32_t* __restrict__ seg, uint32_t M, uint32_t* __restrict__ bad_msm) {
+    uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    fe x, y, t;
+    bool ok = ristretto_decode(x, y, t, w);
+    ge_niels q;
+    if (ok) ge_to_niels_affine(q, x, y, t);
+    else {
+        ge_niels_identity(q);
+        atomicMin(bad, index_base + (unsigned long long)i);
+        if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;    // batch mode: only that MSM is void
+    }
+    st_niels(table, i, q);
+}
 // Each thread decodes points 2t and 2t+1 with one interleaved exponentiation chain (ZK_DEC_PAIR), see fe2.
 __global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
                                                     unsigned long long* __restrict__ bad, unsigned long long index_base,
@@ -153,18 +170,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint4* __restrict__ in
 #else
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
-    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    fe x, y, t;
-    bool ok = ristretto_decode(x, y, t, w);
-    ge_niels q;
-    if (ok) ge_to_niels_affine(q, x, y, t);
-    else {
-        ge_niels_identity(q);
-        atomicMin(bad, index_base + (unsigned long long)i);
-        if (bad_msm) bad_msm[segment_of(seg, M, (uint32_t)(index_base + i))] = 1u;
-    }
-    st_niels(table, i, q);
+    decompress_one(in, i, table, bad, index_base, seg, M, bad_msm);
 #endif
 }
 
@@ -359,6 +365,27 @@ __global__ void __launch_bounds__(256) k_digit_hist(const uint4* __restrict__ sc
     }
 }
 
+// The digits of one (reduced) scalar go to their buckets' entry runs: entry = point index | sign.  ZK_SCATTER_BATCH
+// windows at a time: their returning atomics are issued back to back, then the stores.
+// Precomputed mode (win_stride != 0): window w of point p is row w*win_stride + p of the expanded table (= 2^(c*w) * P)
+// and all windows share the bucket set `wbase`.
+__device__ __forceinline__ void scatter_digits(const uint32_t* s, uint32_t pidx, size_t wbase, int c, int W, uint32_t win_stride,
+                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    uint32_t carry = 0; const int B = 1 << (c - 1);
+    for (int w0 = 0; w0 < W; w0 += ZK_SCATTER_BATCH) {
+        uint32_t pos[ZK_SCATTER_BATCH], val[ZK_SCATTER_BATCH];
+#pragma unroll
+        for (int k = 0; k < ZK_SCATTER_BATCH; k++) {
+            int w = w0 + k;
+            int d = w < W ? next_digit(s, window_geom(W, w), carry) : 0;
+            val[k] = d != 0 ? ((pidx + (uint32_t)w * win_stride) | (d < 0 ? 0x80000000u : 0u)) : 0xffffffffu;
+            pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + (win_stride ? 0 : w)) * B + (abs(d) - 1)], 1u) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < ZK_SCATTER_BATCH; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
+    }
+}
+
 __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__ scalars, size_t n, int c, int W,
                                                        const uint32_t* __restrict__ seg, uint32_t M, int shared_points,
                                                        uint32_t win_stride, uint32_t* __restrict__ cursor,
@@ -368,27 +395,34 @@ __global__ void __launch_bounds__(256) k_digit_scatter(const uint4* __restrict__
     uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
     uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     scalar_reduce(s);
-    uint32_t carry = 0; int B = 1 << (c - 1);
     uint32_t m = seg ? segment_of(seg, M, (uint32_t)i) : 0u;
     const int wpm = win_stride ? 1 : W;
-    size_t wbase = (size_t)m * wpm;
     // the point of term i: the i-th point, or (every MSM of the batch runs over the SAME points) the (i - seg[m])-th
     uint32_t pidx = shared_points ? (uint32_t)i - seg[m] : (uint32_t)i;
-    // ZK_SCATTER_BATCH windows at a time: their returning atomics are issued back to back, then the stores
-    for (int w0 = 0; w0 < W; w0 += ZK_SCATTER_BATCH) {
-        uint32_t pos[ZK_SCATTER_BATCH], val[ZK_SCATTER_BATCH];
-#pragma unroll
-        for (int k = 0; k < ZK_SCATTER_BATCH; k++) {
-            int w = w0 + k;
-            int d = w < W ? next_digit(s, window_geom(W, w), carry) : 0;
-            // precomputed mode: window w of point p is row w*win_stride + p of the expanded table (= 2^(c*w) * P)
-            val[k] = d != 0 ? ((pidx + (uint32_t)w * win_stride) | (d < 0 ? 0x80000000u : 0u)) : 0xffffffffu;
-            pos[k] = d != 0 ? atomicAdd(&cursor[(wbase + (win_stride ? 0 : w)) * B + (abs(d) - 1)], 1u) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < ZK_SCATTER_BATCH; k++) if (val[k] != 0xffffffffu) entries[pos[k]] = val[k];
-    }
+    scatter_digits(s, pidx, (size_t)m * wpm, c, W, win_stride, cursor, entries);
 }
+
+// Decode + scatter in one kernel, for points that arrive compressed together with their scalars (zk_msm_vartime, the
+// dynamic suffix of zk_msm_vartime_mixed): thread i decodes encoding i of the chunk and then scatters the digits of
+// that term's scalar.  The decoder is bound by the integer-multiply pipe and issues no memory traffic; the scatter is
+// bound by the load/store unit (16 returning atomics + 16 scattered stores per term): inside one kernel the second
+// hides under the first, which separate kernels of one stream cannot do (and kernels of different streams do not
+// co-reside).  `scalars` = the scalars of the chunk's terms, `pidx_base` = point index of its
+// first term.  The histogram and the scan must be complete (cursor = bucket offsets).
+#if !ZK_DEC_PAIR
+__global__ void __launch_bounds__(128) k_decompress_scatter(const uint4* __restrict__ in, size_t n, uint4* __restrict__ table,
+                                                            unsigned long long* __restrict__ bad, unsigned long long index_base,
+                                                            const uint4* __restrict__ scalars, uint32_t pidx_base, int c, int W,
+                                                            uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    decompress_one(in, i, table, bad, index_base, nullptr, 0, nullptr);
+    uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
+    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    scalar_reduce(s);
+    scatter_digits(s, pidx_base + (uint32_t)i, 0, c, W, 0u, cursor, entries);
+}
+#endif
 
 // ---- scan + task planning (3 phases, SCAN_TILE-bucket tiles) -----------------------------------------
 // Besides the exclusive scan of the bucket counts (-> offsets into `entries`), the same three passes split
@@ -1033,6 +1067,7 @@ extern "C" int zk_ctx_create(int device, zk_ctx** out) {
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
 #if ZK_TAIL_HP
     if (e == cudaSuccess) {
         int lo = 0, hi = 0;
@@ -1074,6 +1109,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     }
     for (int i = 0; i < 2; i++) { if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
     if (ctx->tail) { cudaStreamSynchronize(ctx->tail); cudaStreamDestroy(ctx->tail); }
     if (ctx->ev_acc) cudaEventDestroy(ctx->ev_acc);
     if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
@@ -1561,8 +1597,44 @@ static int msm_plan(zk_ctx* ctx, size_t n, size_t nmsm, const Precomp* pc, MsmPl
 // scalars: n*32 B in HBM.  Point i lives at tab_a[i] for i < split, tab_b[i - split] otherwise.
 // Batch mode (nmsm > 1): seg_dev = nmsm+1 offsets in HBM; out_ext_dev receives nmsm extended points.
 // fused_out32 != nullptr (single MSM only): the tail also encodes, into that device buffer (k_combine_encode).
+// Dynamic (compressed) points whose upload + decode is queued INSIDE the pipeline, after the scan, with their share of
+// the digit scatter fused into the decoder (k_decompress_scatter).  Worth it from ZK_FUSE_SCATTER_MIN points on: below,
+// making the decoder wait for the histogram costs more latency than the hidden scatter saves.
+#ifndef ZK_FUSE_SCATTER
+#define ZK_FUSE_SCATTER 1
+#endif
+constexpr size_t ZK_FUSE_SCATTER_MIN = (size_t)1 << 17;
+struct FusedDyn { const uint8_t* points32_host = nullptr; size_t n = 0; };
+static inline bool fuse_scatter_pays(size_t n_dyn) { return ZK_FUSE_SCATTER && !ZK_DEC_PAIR && n_dyn >= ZK_FUSE_SCATTER_MIN; }
+
+#if !ZK_DEC_PAIR
+// Chunks alternate between the two side streams (copy of chunk i+1 under the decode of chunk i); each chunk's kernel waits
+// for `ready` (histogram + scan done: cursor holds the bucket offsets).  Term k of the dynamic part is term n_static + k
+// of the MSM.  ctx->ev_fork must have been recorded on the main stream after ctx->bad was reset.
+static int launch_decode_scatter(zk_ctx* ctx, const FusedDyn& fd, size_t n_static, const void* scalars_dev, int c, int W1, cudaEvent_t ready) {
+    const size_t chunk = decode_chunk(ctx, fd.n);
+    int which = 0;
+    ctx->join_aux = true;          // from here on an error return must quiesce() the side streams
+    for (size_t lo = 0; lo < fd.n; lo += chunk, which ^= 1) {
+        size_t cnt = fd.n - lo < chunk ? fd.n - lo : chunk;
+        cudaStream_t sa = ctx->aux[which];
+        if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+        TRY(h2d(ctx, (uint8_t*)ctx->comp.p + lo * 32, fd.points32_host + lo * 32, cnt * 32, sa));
+        if (lo < 2 * chunk) CK(ctx, cudaStreamWaitEvent(sa, ready, 0));
+        k_decompress_scatter<<<grid_for(cnt, 128), 128, 0, sa>>>((const uint4*)ctx->comp.p + lo * 2, cnt, (uint4*)ctx->dyn_table.p + lo * 6,
+                                                                (unsigned long long*)ctx->bad.p, (unsigned long long)lo,
+                                                                (const uint4*)scalars_dev + (n_static + lo) * 2, (uint32_t)(n_static + lo), c, W1,
+                                                                (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int i = 0; i < 2; i++) CK(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+    return ZK_OK;
+}
+#endif
+
 static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, const uint4* tab_a, const uint4* tab_b, size_t split,
-                       void* out_ext_dev, const uint32_t* seg_dev = nullptr, bool shared_points = false, void* fused_out32 = nullptr) {
+                       void* out_ext_dev, const uint32_t* seg_dev = nullptr, bool shared_points = false, void* fused_out32 = nullptr,
+                       const FusedDyn* fd = nullptr) {
     cudaStream_t st = ctx->stream;
     const size_t n = p.n, nmsm = p.nmsm;
     if (n == 0) {
@@ -1604,10 +1676,20 @@ static int msm_enqueue(zk_ctx* ctx, const MsmPlan& p, const void* scalars_dev, c
                                                     (uint32_t*)ctx->offsets.p, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->task_off.p,
                                                     (uint32_t*)ctx->plan.p, (uint2*)ctx->tasks.p);
     LAUNCH_CHECK(ctx);
-    k_digit_scatter<<<grid_for(n, ZK_SORT_BLOCK), ZK_SORT_BLOCK, 0, st>>>((const uint4*)scalars_dev, n, c, W1, seg_dev, (uint32_t)nmsm, shared_points ? 1 : 0, win_stride,
-                                                       (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
-    LAUNCH_CHECK(ctx);
+    // terms whose points are cached are scattered here; dynamic terms with a fused decoder (fd) scatter themselves
+    const size_t n_scatter = fd ? n - fd->n : n;
+    if (n_scatter) {
+        k_digit_scatter<<<grid_for(n_scatter, ZK_SORT_BLOCK), ZK_SORT_BLOCK, 0, st>>>((const uint4*)scalars_dev, n_scatter, c, W1, seg_dev, (uint32_t)nmsm,
+                                                           shared_points ? 1 : 0, win_stride, (uint32_t*)ctx->cursor.p, (uint32_t*)ctx->entries.p);
+        LAUNCH_CHECK(ctx);
+    }
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[2], st));
+#if !ZK_DEC_PAIR
+    if (fd) {
+        CK(ctx, cudaEventRecord(ctx->ev_scan, st));
+        TRY(launch_decode_scatter(ctx, *fd, n - fd->n, scalars_dev, c, W1, ctx->ev_scan));
+    }
+#endif
 #if ZK_TAIL_HP >= 2
     CK(ctx, cudaEventRecord(ctx->ev_sort, st));
     st = st_bulk;
@@ -1781,7 +1863,11 @@ static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int np
     cudaStream_t st = ctx->stream;
     if (ctx->profiling) CK(ctx, cudaEventRecord(ctx->ev[0], st));
     CK(ctx, cudaMemsetAsync(ctx->bad.p, 0xff, 8, st));
-    TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
+    // large dynamic parts: the decoder is queued inside the pipeline (after the scan) and scatters its own terms' digits
+    const bool fuse = !use_pc && fuse_scatter_pays(n_dyn);
+    FusedDyn fd; fd.points32_host = points_dyn32_host; fd.n = n_dyn;
+    if (fuse) CK(ctx, cudaEventRecord(ctx->ev_fork, st));
+    else TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
     size_t pos = 0;
     for (int k = 0; k < npieces; k++) {
         TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + pos, pieces[k].host, pieces[k].bytes, st));
@@ -1790,7 +1876,7 @@ static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int np
     TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
     TRY(msm_enqueue(ctx, plan, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, ctx->out_ext.p, nullptr, false,
-                    fuse_encode ? ctx->out32.p : nullptr));
+                    fuse_encode ? ctx->out32.p : nullptr, fuse ? &fd : nullptr));
     if (ctx->profiling && n == 0) for (int i = 1; i < 4; i++) CK(ctx, cudaEventRecord(ctx->ev[i], st));
     CK(ctx, cudaMemcpyAsync(ctx->h_out + 32, ctx->bad.p, 8, cudaMemcpyDeviceToHost, st));    // after the join inside the pipeline
     return ZK_OK;
