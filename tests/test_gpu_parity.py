@@ -575,3 +575,38 @@ def test_contexts_in_flight_match_oracle(c_oracle):
     assert all(bytes(o) == want for o in outs)
     for t in tabs: t.close()
     for cx in ctxs: cx.close()
+
+
+def test_fused_decode_scatter_pinned_sources(ctx, c_oracle, rfc_vectors):
+    """Page-locked sources of >= 2^17 compressed points take the fused route (k_decompress_scatter: the decoder scatters
+    its own terms' digits, queued after the scan); pageable sources keep the separate scatter.  Same bytes, both routes,
+    against the oracle: plain, with a cached static prefix, and with one invalid encoding."""
+    import zkvm_b200 as zk
+    n = (1 << 17) + 333
+    pts = np.frombuffer(make_points(c_oracle, n, 77), dtype=np.uint8).copy()
+    sc = rand_scalars(n, 77).reshape(-1).copy()
+    want = c_oracle.msm(sc, pts, n, threads=8)
+    zk.host_register(pts); zk.host_register(sc)
+    try:
+        fused = zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)
+        assert fused is not None and bytes(fused) == want
+        # static prefix from a cached table + the same dynamic suffix
+        m = 1000
+        pre_pts = make_points(c_oracle, m, 78); pre_sc = rand_scalars(m, 78)
+        tab = zk.PointTable(ctx, m).append_compressed(pre_pts)
+        got = zk.RistrettoPoint.mixed_multiscalar_mul(ctx, pre_sc, tab, sc, pts)
+        all_sc = np.concatenate([pre_sc.reshape(-1), sc]); all_pts = np.concatenate([np.frombuffer(pre_pts, dtype=np.uint8), pts])
+        assert got is not None and bytes(got) == c_oracle.msm(all_sc, all_pts, m + n, threads=8)
+        # one bad encoding deep inside the dynamic part
+        bad = pts.copy(); zk.host_register(bad)
+        try:
+            k = (1 << 16) + 17
+            bad[32 * k:32 * k + 32] = np.frombuffer(H(rfc_vectors["bad_encodings"]["non_canonical"][0]), dtype=np.uint8)
+            assert zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, bad) is None
+        finally:
+            zk.host_unregister(bad)
+        assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc, pts)) == want      # the context stays usable
+    finally:
+        zk.host_unregister(pts); zk.host_unregister(sc)
+    # the pageable route (staging ring, separate scatter) on the same bytes
+    assert bytes(zk.RistrettoPoint.optional_multiscalar_mul(ctx, np.array(sc), np.array(pts))) == want
