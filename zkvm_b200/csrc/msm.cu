@@ -1292,6 +1292,7 @@ static int h2d(zk_ctx* ctx, void* dst, const uint8_t* src, size_t bytes, cudaStr
 // After a failure between the fork onto the side streams and the join: let everything queued drain, so that no copy
 // still reads the caller's buffers and no decoder still writes ctx->bad when the next call starts.
 static void quiesce(zk_ctx* ctx) {
+    if (ctx->tail) cudaStreamSynchronize(ctx->tail);     // a failed call may have left the hop back to the main stream unqueued
     for (int i = 0; i < 2; i++) if (ctx->aux[i]) cudaStreamSynchronize(ctx->aux[i]);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->join_aux = false;
@@ -1787,7 +1788,9 @@ extern "C" int zk_msm_table_dev(zk_ctx* ctx, const void* scalars32_dev, const zk
     MsmPlan plan;
     TRY(msm_plan(ctx, n, 1, use_pc ? &pc : nullptr, &plan));
     if (ctx->profiling) { CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream)); }
-    return msm_enqueue(ctx, plan, scalars32_dev, t->d + offset * 6, nullptr, n, out_ext128_dev);
+    int rc = msm_enqueue(ctx, plan, scalars32_dev, t->d + offset * 6, nullptr, n, out_ext128_dev);
+    if (rc != ZK_OK) quiesce(ctx);      // the phases hop between two streams: leave none of them running behind an error
+    return rc;
 }
 
 #ifdef ZK_TIMELINE
