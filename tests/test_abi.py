@@ -89,3 +89,19 @@ def test_rust_sys_matches_header():
             if not is_ptr_c:
                 size = {"c_int": 4, "usize": 8, "u64": 8, "f32": 4, "f64": 8}[rp.split(":")[1].strip()]
                 assert C.sizeof(ct) == size, (name, ctype, rp)
+
+
+def test_library_sets_hardware_queue_default_only_when_unset():
+    """Loading libzkmsm.so gives CUDA_DEVICE_MAX_CONNECTIONS a default of 32 (four streams per context, several contexts
+    in flight: DESIGN.md section 5.4) and never overrides the application's own setting."""
+    import subprocess
+    import sys
+    from zkvm_b200 import _lib
+    code = ("import ctypes, sys; ctypes.CDLL(sys.argv[1]); libc = ctypes.CDLL(None); libc.getenv.restype = ctypes.c_char_p; "
+            "print((libc.getenv(b'CUDA_DEVICE_MAX_CONNECTIONS') or b'').decode())")
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    out = subprocess.run([sys.executable, "-c", code, _lib.LIB_PATH], env=env, capture_output=True, text=True, check=True)
+    assert out.stdout.strip() == "32"
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "8"
+    out = subprocess.run([sys.executable, "-c", code, _lib.LIB_PATH], env=env, capture_output=True, text=True, check=True)
+    assert out.stdout.strip() == "8"
