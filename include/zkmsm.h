@@ -61,7 +61,11 @@ int zk_ctx_sync(zk_ctx* ctx);
  * event (about 0.3 ms more latency per call, no CPU while waiting).  Use 1 when more calls are in flight on the host
  * than it has cores to spare (several contexts per GPU x several GPUs): a spinning waiter occupies a core. */
 int zk_ctx_set_wait(zk_ctx* ctx, int mode);
-/* cudaStream_t of the ctx as an opaque pointer (for CUDA-event timing by the caller). */
+/* cudaStream_t of the ctx as an opaque pointer: the MAIN stream, on which every asynchronous entry point (zk_*_dev) is
+ * ordered -- work queued on it afterwards sees the call's result, events recorded on it bracket the call.  Internally a
+ * call also uses two decode side streams and a high-priority stream for its short latency-bound phases; the main stream
+ * waits for them, so callers never see them.  The main stream has low priority: latency-critical follow-up work (e.g. a
+ * 128-byte gather of partials) is better issued on a high-priority stream of the caller's that waits on this one. */
 void* zk_ctx_stream(zk_ctx* ctx);
 /* high = 1: recreate the ctx's streams with the device's highest stream priority, so that its (small) kernels are
  * scheduled ahead of other contexts' bulk work; 0 restores the default.  Call while the ctx is idle. */
