@@ -1873,14 +1873,16 @@ static int enqueue_partial_impl(zk_ctx* ctx, const zk_host_piece* pieces, int np
     const bool fuse = !use_pc && fuse_scatter_pays(n_dyn) && !would_stage(ctx, points_dyn32_host, n_dyn * 32) &&
                       !would_stage(ctx, scalars_dyn32_host, n_dyn * 32);
     FusedDyn fd; fd.points32_host = points_dyn32_host; fd.n = n_dyn;
-    if (fuse) CK(ctx, cudaEventRecord(ctx->ev_fork, st));
-    else TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
+    if (!fuse) TRY(start_upload_decode(ctx, points_dyn32_host, n_dyn, nullptr, 0, nullptr));
     size_t pos = 0;
     for (int k = 0; k < npieces; k++) {
         TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + pos, pieces[k].host, pieces[k].bytes, st));
         pos += pieces[k].bytes;
     }
     TRY(h2d(ctx, (uint8_t*)ctx->scalars.p + n_static * 32, scalars_dyn32_host, n_dyn * 32, st));
+    // fused route: the decoder's first chunk needs EVERY scalar (the histogram), so the scalars cross the link first and
+    // alone; the side streams' point copies fork off behind them instead of sharing the link with them
+    if (fuse) CK(ctx, cudaEventRecord(ctx->ev_fork, st));
     const uint4* ta = n_static ? t->d + offset * 6 : (const uint4*)ctx->dyn_table.p;
     TRY(msm_enqueue(ctx, plan, ctx->scalars.p, ta, (const uint4*)ctx->dyn_table.p, n_static, ctx->out_ext.p, nullptr, false,
                     fuse_encode ? ctx->out32.p : nullptr, fuse ? &fd : nullptr));
