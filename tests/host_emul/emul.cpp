@@ -4,6 +4,7 @@
 // product library.
 #include <string.h>
 #include "../../zkvm_b200/csrc/ge25519.cuh"
+#include "../../zkvm_b200/csrc/recode.cuh"
 using namespace zk;
 
 static void ld(fe& r, const uint8_t* b) { memcpy(r.v, b, 32); }
@@ -67,5 +68,18 @@ int emul_msm(const uint8_t* scalars, const uint8_t* points, size_t n, uint8_t* o
     }
     uint32_t o[8]; ristretto_encode(o, acc); memcpy(out32, o, 32);
     return 0;
+}
+// the sort kernels' recoding (recode.cuh): scalar32 -> reduced scalar (32 bytes), W signed digits, their offsets and widths
+void emul_recode(const uint8_t* scalar32, int W, uint8_t* reduced32, int32_t* digits, int32_t* offs, int32_t* widths) {
+    uint32_t s[8]; memcpy(s, scalar32, 32);
+    scalar_reduce(s);
+    memcpy(reduced32, s, 32);
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        win_geom g = window_geom(W, w);
+        digits[w] = next_digit(s, g, carry);
+        offs[w] = g.off; widths[w] = g.width;
+    }
+    digits[W] = (int32_t)carry;      // must be 0: the 254th bit absorbs the top digit's carry
 }
 }

@@ -94,3 +94,28 @@ def test_group_law_msm(emul, sodium_vectors):
         o = C.create_string_buffer(32)
         assert emul.emul_msm(s, p, C.c_size_t(n), o) == 0
         assert o.raw.hex() == case["result"]
+
+
+def test_scalar_recoding(emul):
+    """recode.cuh (the code the sort kernels run): reduction mod l of any 256-bit string, balanced window geometry
+    covering 254 bits, signed digits within half a window, and  sum_w d_w 2^(off_w) == s mod l  with no carry left --
+    for every window count the library can pick or be forced to (c = 4..20) and edge scalars around l and 2^256."""
+    L = 2**252 + 27742317777372353535851937790883648493
+    rnd = random.Random(9)
+    edge = [0, 1, 2, L - 1, L, L + 1, 2 * L, 8 * L, 8 * L - 1, 15 * L + 5, 2**252 - 1, 2**252, 2**253 - 1, 2**253, 2**255, 2**256 - 1,
+            (2**256 - 1) // 3, 2**128, 2**128 - 1] + [(1 << k) - 1 for k in range(1, 256, 17)] + [1 << k for k in range(0, 256, 13)]
+    # all-ones windows provoke the longest carry runs; 0x8000.. patterns sit exactly on the half-window boundary
+    edge += [int("8" + "0" * 63, 16) % 2**256, int("7f" * 32, 16), int("80" * 32, 16), int("ff" * 32, 16) % L, L // 2, L // 2 + 1]
+    scalars = edge + [rnd.getrandbits(256) for _ in range(300)] + [rnd.getrandbits(253) for _ in range(100)]
+    red = C.create_string_buffer(32)
+    for c in range(4, 21):
+        W = (254 + c - 1) // c
+        dig = (C.c_int32 * (W + 1))(); off = (C.c_int32 * W)(); wid = (C.c_int32 * W)()
+        for s in scalars:
+            emul.emul_recode(s.to_bytes(32, "little"), W, red, dig, off, wid)
+            assert int.from_bytes(red.raw, "little") == s % L
+            assert dig[W] == 0, (c, hex(s))
+            assert off[0] == 0 and all(off[w + 1] == off[w] + wid[w] for w in range(W - 1)) and off[W - 1] + wid[W - 1] == 254
+            assert max(wid) - min(wid) <= 1 and max(wid) == (254 + W - 1) // W
+            assert all(abs(dig[w]) <= 1 << (wid[w] - 1) for w in range(W)), (c, hex(s))
+            assert sum(dig[w] << off[w] for w in range(W)) == s % L, (c, hex(s))
