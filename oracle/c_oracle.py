@@ -76,3 +76,9 @@ def point_sum(points, n: int):
 
 def is_valid(p32: bytes) -> bool:
     return bool(load().oracle_is_valid(p32))
+
+
+def set_vector(on: bool) -> bool:
+    """Select the 4-lane AVX-512 IFMA bucket accumulation (dalek's vector-backend shape) for the Pippenger MSMs of this
+    process.  Returns whether it is in use (False on a CPU without IFMA: the scalar radix-2^51 code keeps running)."""
+    return bool(load().oracle_set_vector(1 if on else 0))

@@ -23,8 +23,12 @@
  *   otherwise: Pippenger, signed radix-2^w digits, w = 6 (n<500), 7 (n<800), 8 above; per digit
  *              column fill 2^(w-1) buckets, running-sum them, Horner over columns by w doublings.
  * Field arithmetic: radix-2^51, five 64-bit limbs, 128-bit products (dalek's `u64` serial
- * backend shape).  dalek's AVX2/IFMA vector backends cannot be reproduced here (no Rust);
- * DESIGN.md states this next to every CPU number.
+ * backend shape).  This serial code is THE checker: every parity gate and test compares against it.
+ * For the TIMING arm only there is also a vector path in the shape of dalek's AVX2/IFMA backends
+ * (four coordinates of a point in the four lanes of a vector, AVX-512 IFMA, bucket accumulation
+ * only; see "optional 4-lane IFMA bucket accumulation" below), selected with oracle_set_vector()
+ * where the CPU has IFMA and checked against the serial code in tests/test_oracle.py.  dalek's
+ * own backends cannot be built here (no Rust); DESIGN.md states this next to every CPU number.
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -341,9 +345,135 @@ static void msm_pippenger(ge* out, const uint8_t* scalars, const ge* pts, size_t
     *out = total;
     free(digits); free(cached); free(buckets);
 }
+/* ---- optional 4-lane IFMA bucket accumulation -------------------------------------------------------------------
+ * dalek ships vector backends (AVX2, AVX-512 IFMA) that hold the four coordinates of a point in the four 64-bit lanes
+ * of a vector and run the HWCD addition as two 4-way field multiplications plus lane shuffles.  This is that shape for
+ * the one loop that dominates a Pippenger MSM -- bucket[digit] += cached point -- on AVX-512 IFMA (vpmadd52luq/huq,
+ * radix 2^51, five limbs per lane); bucket reduction and the Horner over columns stay scalar (2^w additions and w
+ * doublings per column against n).  Selected at run time (oracle_set_vector) and only where the CPU has it; checked
+ * against the scalar path in tests/test_oracle.py.  It exists so that the CPU baseline can also be quoted for the
+ * reference's vectorised build, not only for its default serial one ("AVX2/IFMA backend as built", BASELINE.json). */
+static int g_use_vec = 0;
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define VEC __attribute__((target("avx2,avx512f,avx512vl,avx512ifma")))
+typedef struct { __m256i l[5]; } f4;          /* lanes: X, Y, T, Z -- or, cached: Y-X, Y+X, 2dT, 2Z */
+static int vec_available(void) {
+    return __builtin_cpu_supports("avx512ifma") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx2");
+}
+VEC static inline __m256i v_mul19(__m256i v) { return _mm256_add_epi64(_mm256_add_epi64(_mm256_slli_epi64(v, 4), _mm256_slli_epi64(v, 1)), v); }
+/* limbs < 2^62 in, limbs < 2^51 + 2^15 out */
+VEC static inline void f4_carry(f4* a) {
+    const __m256i mask = _mm256_set1_epi64x((long long)M51);
+    __m256i c;
+    c = _mm256_srli_epi64(a->l[0], 51); a->l[0] = _mm256_and_si256(a->l[0], mask); a->l[1] = _mm256_add_epi64(a->l[1], c);
+    c = _mm256_srli_epi64(a->l[1], 51); a->l[1] = _mm256_and_si256(a->l[1], mask); a->l[2] = _mm256_add_epi64(a->l[2], c);
+    c = _mm256_srli_epi64(a->l[2], 51); a->l[2] = _mm256_and_si256(a->l[2], mask); a->l[3] = _mm256_add_epi64(a->l[3], c);
+    c = _mm256_srli_epi64(a->l[3], 51); a->l[3] = _mm256_and_si256(a->l[3], mask); a->l[4] = _mm256_add_epi64(a->l[4], c);
+    c = _mm256_srli_epi64(a->l[4], 51); a->l[4] = _mm256_and_si256(a->l[4], mask); a->l[0] = _mm256_add_epi64(a->l[0], v_mul19(c));
+}
+/* r = x * y lane by lane; limbs of x, y < 2^52.  x_i y_j = lo52 + 2^52 hi52 and 2^52 = 2 * 2^51: the high halves go to
+ * the next limb doubled; limbs 5..9 fold back with 2^255 = 19. */
+VEC static inline void f4_mul(f4* r, const f4* x, const f4* y) {
+    const __m256i zero = _mm256_setzero_si256();
+    __m256i lo[9], hi[9], z[10];
+    for (int k = 0; k < 9; k++) { lo[k] = zero; hi[k] = zero; }
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) {
+            lo[i + j] = _mm256_madd52lo_epu64(lo[i + j], x->l[i], y->l[j]);
+            hi[i + j] = _mm256_madd52hi_epu64(hi[i + j], x->l[i], y->l[j]);
+        }
+    z[0] = lo[0];
+    for (int k = 1; k < 9; k++) z[k] = _mm256_add_epi64(lo[k], _mm256_slli_epi64(hi[k - 1], 1));
+    z[9] = _mm256_slli_epi64(hi[8], 1);
+    for (int k = 0; k < 5; k++) r->l[k] = _mm256_add_epi64(z[k], v_mul19(z[k + 5]));     /* < 2^56 + 19 * 2^56 */
+    f4_carry(r);
+}
+/* 2p, limb by limb: keeps a - b + 2p non-negative for limbs a, b < 2^51 + 2^15 */
+VEC static inline __m256i v_bias(int limb) { return _mm256_set1_epi64x(limb == 0 ? 0xfffffffffffdaLL : 0xffffffffffffeLL); }
+/* acc += q (cached: Y-X, Y+X, 2dT, 2Z), the unified a = -1 extended addition as two 4-way multiplications */
+VEC static inline void f4_add_cached(f4* acc, const f4* q) {
+    f4 u, m, t, L, R;
+    for (int i = 0; i < 5; i++) {
+        __m256i p = acc->l[i], ps = _mm256_permute4x64_epi64(p, 0xE1);                     /* (Y, X, T, Z) */
+        __m256i sum = _mm256_add_epi64(p, ps), dif = _mm256_add_epi64(_mm256_sub_epi64(ps, p), v_bias(i));
+        u.l[i] = _mm256_blend_epi32(_mm256_blend_epi32(p, dif, 0x03), sum, 0x0C);          /* Y-X | Y+X | T | Z */
+    }
+    f4_carry(&u);
+    f4_mul(&m, &u, q);                                                                       /* A | B | C | D */
+    for (int i = 0; i < 5; i++) {
+        __m256i v = m.l[i], vs = _mm256_permute4x64_epi64(v, 0xB1);                        /* (B, A, D, C) */
+        __m256i sum = _mm256_add_epi64(v, vs), dif = _mm256_add_epi64(_mm256_sub_epi64(vs, v), v_bias(i));
+        t.l[i] = _mm256_blend_epi32(sum, dif, 0x33);                                         /* E=B-A | H=A+B | F=D-C | G=C+D */
+    }
+    f4_carry(&t);
+    for (int i = 0; i < 5; i++) {
+        L.l[i] = _mm256_permute4x64_epi64(t.l[i], 0x8C);                                     /* E | G | E | F */
+        R.l[i] = _mm256_permute4x64_epi64(t.l[i], 0xD6);                                     /* F | H | H | G */
+    }
+    f4_mul(acc, &L, &R);                                                                     /* X3=EF | Y3=GH | T3=EH | Z3=FG */
+}
+/* -q: swap Y-X and Y+X, negate 2dT */
+VEC static inline void f4_neg_cached(f4* r, const f4* q) {
+    for (int i = 0; i < 5; i++) {
+        __m256i s = _mm256_permute4x64_epi64(q->l[i], 0xE1);
+        r->l[i] = _mm256_blend_epi32(s, _mm256_sub_epi64(v_bias(i), s), 0x30);             /* lane 2 (T) = 2p - t, < 2^52 */
+    }
+}
+VEC static void f4_pack(f4* r, const fe* a, const fe* b, const fe* c, const fe* d) {
+    for (int i = 0; i < 5; i++) r->l[i] = _mm256_set_epi64x((long long)d->v[i], (long long)c->v[i], (long long)b->v[i], (long long)a->v[i]);
+}
+VEC static void msm_pippenger_vec(ge* out, const uint8_t* scalars, const ge* pts, size_t n) {
+    int w = n < 500 ? 6 : n < 800 ? 7 : 8;
+    int nb = 1 << (w - 1);
+    int max_digits = (256 + w - 1) / w + 1;
+    int8_t* digits = malloc(n * (size_t)max_digits);
+    f4* cached = aligned_alloc(32, n * sizeof(f4));
+    f4* buckets = aligned_alloc(32, nb * sizeof(f4));
+    int count = max_digits;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t s[4]; sc_reduce256(s, scalars + 32 * i);
+        count = sc_radix_2w(digits + i * max_digits, s, w);
+        fe ymx, ypx, t2d, z2;
+        fe_sub(&ymx, &pts[i].Y, &pts[i].X); fe_add(&ypx, &pts[i].Y, &pts[i].X); fe_carry(&ypx);
+        fe_mul(&t2d, &pts[i].T, &FE_D2); fe_add(&z2, &pts[i].Z, &pts[i].Z); fe_carry(&z2);
+        f4_pack(&cached[i], &ymx, &ypx, &t2d, &z2);
+    }
+    f4 ident; f4_pack(&ident, &FE_ZERO, &FE_ONE, &FE_ZERO, &FE_ONE);
+    ge total; ge_identity(&total);
+    for (int col = count - 1; col >= 0; col--) {
+        for (int b = 0; b < nb; b++) buckets[b] = ident;
+        for (size_t i = 0; i < n; i++) {
+            int d = digits[i * max_digits + col];
+            if (d > 0) f4_add_cached(&buckets[d - 1], &cached[i]);
+            else if (d < 0) { f4 nq; f4_neg_cached(&nq, &cached[i]); f4_add_cached(&buckets[-d - 1], &nq); }
+        }
+        /* back to the scalar representation for the running sums */
+        ge run, sum;
+        for (int b = nb - 1; b >= 0; b--) {
+            uint64_t lane[5][4]; ge g;
+            for (int i = 0; i < 5; i++) _mm256_storeu_si256((__m256i*)lane[i], buckets[b].l[i]);
+            for (int i = 0; i < 5; i++) { g.X.v[i] = lane[i][0]; g.Y.v[i] = lane[i][1]; g.T.v[i] = lane[i][2]; g.Z.v[i] = lane[i][3]; }
+            if (b == nb - 1) { run = g; sum = g; } else { ge_add(&run, &run, &g); ge_add(&sum, &sum, &run); }
+        }
+        for (int k = 0; k < w; k++) ge_dbl(&total, &total);
+        ge_add(&total, &total, &sum);
+    }
+    *out = total;
+    free(digits); free(cached); free(buckets);
+}
+#else
+static int vec_available(void) { return 0; }
+static void msm_pippenger_vec(ge* out, const uint8_t* scalars, const ge* pts, size_t n) { msm_pippenger(out, scalars, pts, n); }
+#endif
+/* on != 0: use the 4-lane IFMA bucket accumulation where the CPU has it.  Returns whether it is in use. */
+int oracle_set_vector(int on) { g_use_vec = on && vec_available(); return g_use_vec; }
+
 static void msm_single(ge* out, const uint8_t* scalars, const ge* pts, size_t n) {
     if (n == 0) { ge_identity(out); return; }
-    if (n < 190) msm_straus(out, scalars, pts, n); else msm_pippenger(out, scalars, pts, n);
+    if (n < 190) msm_straus(out, scalars, pts, n);
+    else if (g_use_vec) msm_pippenger_vec(out, scalars, pts, n);
+    else msm_pippenger(out, scalars, pts, n);
 }
 
 typedef struct { const uint8_t* scalars; const ge* pts; size_t n; ge out; } msm_job;

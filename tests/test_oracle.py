@@ -133,3 +133,47 @@ def test_even_subgroup_criterion():
             assert is_square(pt.Z * pt.Z - pt.Y * pt.Y) == (k % 2 == 0)
             if k % 2 == 0:
                 assert pt.encode() == base.encode()     # adding 4-torsion stays in the same ristretto coset
+
+
+def test_c_vector_backend_matches_serial(c_oracle, sodium_vectors):
+    """The 4-lane AVX-512 IFMA bucket accumulation of the C port (timing arm only; dalek's vector-backend shape) gives the
+    same bytes as the serial radix-2^51 code it stands beside: random and adversarial scalars, every Pippenger width,
+    one and several threads, and the libsodium known answers.  Without IFMA the switch must simply refuse."""
+    have = c_oracle.set_vector(True)
+    c_oracle.set_vector(False)
+    if not have:
+        assert c_oracle.set_vector(True) is False
+        pytest.skip("host CPU has no AVX-512 IFMA: the vector backend is not selectable here")
+    L = 2**252 + 27742317777372353535851937790883648493
+    rng = np.random.default_rng(31)
+
+    def both(sc, pts, n, threads):
+        c_oracle.set_vector(False); a = c_oracle.msm(sc, pts, n, threads=threads)
+        try:
+            assert c_oracle.set_vector(True); b = c_oracle.msm(sc, pts, n, threads=threads)
+        finally:
+            c_oracle.set_vector(False)
+        assert a is not None and a == b, (n, threads)
+        return a
+
+    for n, threads in ((190, 1), (300, 1), (499, 2), (650, 1), (800, 1), (3000, 3), (40000, 4)):
+        pts = c_oracle.from_uniform(rng.integers(0, 256, size=(n, 64), dtype=np.uint8), n)
+        both(rng.integers(0, 256, size=(n, 32), dtype=np.uint8), pts, n, threads)
+        # adversarial scalar sets: one bucket per column, all digits negative, zero, small, around l, unreduced maxima
+        for v in (1, 2, L - 1, L - 2, (L - 1) // 2, int("80" * 32, 16) % L, int("7f" * 31 + "0f", 16), 0, 2**256 - 1, 8 * L + 3):
+            sc = np.frombuffer((v % 2**256).to_bytes(32, "little") * n, dtype=np.uint8)
+            both(sc, pts, n, threads)
+        # repeated points (P + P inside a bucket: the unified addition must double correctly) and P, -P pairs
+        rep = np.frombuffer(bytes(pts[:32]) * n, dtype=np.uint8)
+        both(rng.integers(0, 256, size=(n, 32), dtype=np.uint8), rep, n, threads)
+        sc = rng.integers(0, 256, size=(n // 2, 32), dtype=np.uint8)
+        neg = np.array([(L - int.from_bytes(bytes(r), "little") % L) % L for r in sc], dtype=object)
+        sc2 = np.concatenate([sc.reshape(-1), np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in neg), dtype=np.uint8)])
+        half = np.frombuffer(bytes(pts[: 32 * (n // 2)]), dtype=np.uint8)
+        r = both(sc2, np.concatenate([half, half]), 2 * (n // 2), threads)
+        assert r == bytes(32)                                      # sum s_i P_i + sum (-s_i) P_i = identity
+    for case in sodium_vectors["msm"]:
+        n = len(case["scalars"])
+        s = np.frombuffer(b"".join(H(x) for x in case["scalars"]), dtype=np.uint8)
+        p = np.frombuffer(b"".join(H(x) for x in case["points"]), dtype=np.uint8)
+        assert both(s, p, n, 1).hex() == case["result"]
