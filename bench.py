@@ -535,6 +535,7 @@ def run_cuda(a):
     sweep = None
     if extras and world == 1:
         sweep = []
+        cpu_vec = cpu_vector_backend()
         for lg in range(10, min(a.log2n, 20) + 1):
             m = 1 << lg
             sc_m, pc_m = np_scal[0][: 32 * m], np_comp[0][: 32 * m]
@@ -546,6 +547,7 @@ def run_cuda(a):
             if lg <= 14:                                   # short runs: best of 3
                 for _ in range(2):
                     x = cpu_time_msm(sc_m, pc_m, m, th); dN, mN = min(dN, x[0]), min(mN, x[1])
+            mV = cpu_time_msm(sc_m, pc_m, m, th, vector=True)[1] if cpu_vec else None
             got_t = zk.RistrettoPoint.vartime_multiscalar_mul(ctx, sc_m, tables[0], n=m)
             got_c = zk.RistrettoPoint.optional_multiscalar_mul(ctx, sc_m, pc_m)
             ok = bytes(got_t) == wantm and got_c is not None and bytes(got_c) == wantm
@@ -566,6 +568,7 @@ def run_cuda(a):
             sweep.append({"log2n": lg, "window_bits": zk.pick_window(m), "gpu_ms": gms, "gpu_points_per_s": m / (gms * 1e-3),
                           "gpu_e2e_ms": ems, "gpu_e2e_points_per_s": m / (ems * 1e-3),
                           "cpu_1t_points_per_s": (m / m1) if m1 else None, "cpu_1t_e2e_points_per_s": (m / (d1 + m1)) if m1 else None,
+                          "cpu_Nt_vector_points_per_s": (m / mV) if mV else None,
                           "cpu_Nt_points_per_s": m / mN, "cpu_Nt_e2e_points_per_s": m / (dN + mN), "cpu_threads": th, "parity_ok": ok})
 
     # ---- BASELINE config 5: ONE block-scale MSM of fixed total size across the N GPUs (strong scaling) -----------
